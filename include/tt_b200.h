@@ -1,0 +1,212 @@
+/*
+ * tt_b200.h — C ABI of the B200-native two-tower hot path (libtt_b200.so).
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names.
+ * The reference (freemvmt/two-towers-overlords) is pure Python and has no FFI;
+ * the functions below are what a ctypes binding placed under the reference's
+ * backend/model.py + backend/training.py surface would bind (INTEGRATION.md shows
+ * the stub).  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates);
+ *     the library never allocates or frees persistent memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, non-zero = error; tt_last_error() gives the text
+ *     (thread-local); nothing throws across the boundary;
+ *   - row-major everywhere; H = hidden size of the token table (384 for MiniLM),
+ *     P = projection_dim; all float buffers are fp32 unless a dtype says else.
+ *   - no torch types, no CPU fallback: a call on a machine without an sm_100
+ *     device returns an error.
+ */
+#ifndef TT_B200_H
+#define TT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_B200_VERSION 100 /* major*100 + minor */
+
+typedef void* tt_stream_t; /* cudaStream_t */
+
+/* element types of caller buffers */
+enum tt_dtype {
+  TT_F32 = 0,
+  TT_BF16 = 1,
+  TT_I64 = 2,
+  TT_I32 = 3,
+  TT_U16 = 4,
+  TT_U8 = 5
+};
+
+/* arithmetic of the projection / scan contractions */
+enum tt_precision {
+  TT_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores: strict-parity mode                         */
+  TT_PREC_BF16X3 = 1, /* tcgen05 bf16 MMA, 3-term hi/lo split, fp32 accumulate (~2^-16 rel.) */
+  TT_PREC_BF16 = 2    /* tcgen05 bf16 MMA, single pass, fp32 accumulate (~2^-8 rel.)         */
+};
+
+int tt_version(void);
+const char* tt_last_error(void);
+/* sm count / compute capability of the current device; error if it is not sm_100. */
+int tt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Tower front end: token-row gather + attention-masked mean + L2 normalise.
+ * Replaces backend/model.py:48-56 (tokens→device, `pretrained_model(**tokens)` restated as
+ * E[input_ids] per north_star, `_mean_pooling` model.py:63-72, `F.normalize` model.py:56).
+ *   table [vocab,H] f32|bf16; ids [B,L] i64|i32|u16; mask [B,L] i64|i32|u8 (0 = padding).
+ *   xhat [B,H]: (sum_t m_t E[id_t] / max(sum m, 1e-9)) / max(||.||, 1e-12)
+ *   cnt [B] = sum_t m_t (unclamped); nrm [B] = L2 norm of the mean (unclamped).  cnt/nrm may be NULL.
+ *   err_flag (nullable, device int): set to 1 if any unmasked id is outside [0,vocab).
+ * ---------------------------------------------------------------------------------------- */
+int tt_pool_fwd(const void* table, int table_dtype, int vocab, int H,
+                const void* ids, int ids_dtype, const void* mask, int mask_dtype,
+                int B, int L, float* xhat, float* cnt, float* nrm, int* err_flag,
+                tt_stream_t stream);
+
+/* Up to 4 segments in one launch (query / positive / negative batches of a triplet step). Rows of
+ * segment s land at xhat[row0[s] ..]; segments may use different tables (the reference keeps one
+ * backbone copy per tower, model.py:84-85). */
+typedef struct tt_pool_seg {
+  const void* table;
+  const void* ids;
+  const void* mask;
+  int B;
+  int L;
+  int row0;
+  int _pad;
+} tt_pool_seg;
+int tt_pool_fwd_multi(const tt_pool_seg* segs, int nseg, int table_dtype, int vocab, int H,
+                      int ids_dtype, int mask_dtype, float* xhat, float* cnt, float* nrm,
+                      int* err_flag, tt_stream_t stream);
+
+/* Backward of tt_pool_fwd into the token table (north_star config 3, "trainable table"; the
+ * reference freezes the backbone, model.py:28-30,51 — see DESIGN.md D2).  Deterministic:
+ * (token id, position) pairs are radix-sorted, each touched row is reduced in position order and
+ * written once; no float atomics.
+ *   dxhat, xhat [B,H]; cnt, nrm [B] from the forward; dtable [vocab,H] f32 is OVERWRITTEN
+ *   (zero rows for untouched ids) unless accumulate != 0.
+ *   ws: scratch of at least tt_pool_bwd_ws_bytes(B,L,vocab,H) bytes. */
+size_t tt_pool_bwd_ws_bytes(int B, int L, int vocab, int H);
+int tt_pool_bwd(const float* dxhat, const float* xhat, const float* cnt, const float* nrm,
+                const void* ids, int ids_dtype, const void* mask, int mask_dtype, int B, int L,
+                int vocab, int H, float* dtable, int accumulate, void* ws, size_t ws_bytes,
+                tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Projection MLP of one tower: y = relu(x W1^T + b1) W2^T + b2      (model.py:33-38,59)
+ *   x [M,H]; W1 [P,H]; b1 [P]; W2 [P,P]; b2 [P]; h [M,P] (post-ReLU, saved for backward); y [M,P].
+ *   ws: scratch of tt_mlp_ws_bytes(M,H,P,precision) bytes (0 for TT_PREC_FP32).
+ * ---------------------------------------------------------------------------------------- */
+size_t tt_mlp_ws_bytes(int M, int H, int P, int precision);
+int tt_encode_fwd(const float* x, int M, int H, int P, const float* W1, const float* b1,
+                  const float* W2, const float* b2, float* h, float* y, int precision, void* ws,
+                  size_t ws_bytes, tt_stream_t stream);
+/* Backward of tt_encode_fwd (what autograd does for model.py:59 inside training.py:50).
+ *   dy [M,P]; grads dW1 [P,H], db1 [P], dW2 [P,P], db2 [P] are overwritten, or added to when
+ *   accumulate != 0 (the document tower is called twice per step, training.py:41-42);
+ *   dx [M,H] nullable (only needed when the table trains). */
+int tt_encode_bwd(const float* dy, const float* x, const float* h, const float* W1,
+                  const float* W2, int M, int H, int P, float* dW1, float* db1, float* dW2,
+                  float* db2, float* dx, int accumulate, int precision, void* ws, size_t ws_bytes,
+                  tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cosine triplet loss (model.py:132-145):
+ *   cos(x,y) = sum_i (x_i/max(||x||,1e-8)) (y_i/max(||y||,1e-8))
+ *   hinge_i = relu((1-cos(q_i,p_i)) - (1-cos(q_i,n_i)) + margin);  loss = inv_batch * sum_i hinge_i
+ *   inv_batch = 1/B for one GPU, 1/B_global under data parallelism.
+ *   stats [B,8] = {cos_p, cos_n, hinge, |q|, |p|, |n|, q.p, q.n} saved for backward.
+ * ---------------------------------------------------------------------------------------- */
+int tt_triplet_loss_fwd(const float* q, const float* p, const float* n, int B, int P, float margin,
+                        float inv_batch, float* stats, float* loss, tt_stream_t stream);
+/* dloss: device scalar (upstream gradient of the loss; NULL means 1).  dq/dp/dn [B,P]. */
+int tt_triplet_loss_bwd(const float* q, const float* p, const float* n, const float* stats,
+                        const float* dloss, int B, int P, float inv_batch, float* dq, float* dp,
+                        float* dn, tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One whole triplet training step, forward + backward (training.py:37-50 without the optimiser):
+ * pool(q), pool(p), pool(n) -> both tower MLPs -> loss -> gradients of the 8 projection tensors
+ * (and of the tables when dtable_q/dtable_d are non-NULL).  Gradients are OVERWRITTEN.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tt_step_args {
+  /* tokens */
+  const void* q_ids;  const void* q_mask;  int Lq;
+  const void* p_ids;  const void* p_mask;
+  const void* n_ids;  const void* n_mask;  int Ld;
+  int ids_dtype, mask_dtype;
+  int B;             /* triplets on this GPU                         */
+  /* frozen (or trainable) token tables */
+  const void* table_q; const void* table_d; int table_dtype; int vocab; int H;
+  /* projection parameters, fp32 */
+  int P;
+  const float *Wq1, *bq1, *Wq2, *bq2, *Wd1, *bd1, *Wd2, *bd2;
+  /* loss */
+  float margin; float inv_batch; float grad_scale; /* upstream d(loss) (1 normally)  */
+  /* outputs */
+  float* loss;       /* [1]                                          */
+  float *dWq1, *dbq1, *dWq2, *dbq2, *dWd1, *dbd1, *dWd2, *dbd2;
+  float *dtable_q, *dtable_d; /* nullable                            */
+  int* err_flag;     /* nullable                                     */
+  int precision;
+  void* ws; size_t ws_bytes;  /* >= tt_step_ws_bytes(...)            */
+} tt_step_args;
+size_t tt_step_ws_bytes(int B, int Lq, int Ld, int H, int P, int vocab, int precision,
+                        int train_table);
+int tt_triplet_step(const tt_step_args* args, tt_stream_t stream);
+
+/* Adam update, same arithmetic as torch.optim.Adam defaults used at training.py:436
+ * (betas 0.9/0.999, eps 1e-8, no weight decay, no amsgrad): n fp32 elements, `step` is the
+ * 1-based step count AFTER this update.  grad_scale multiplies the gradient first (e.g. 1/world). */
+int tt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                 float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                 tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Retrieval / evaluation (training.py:244-311 restated as a batched exhaustive scan).
+ * ---------------------------------------------------------------------------------------- */
+/* y[i,:] = x[i,:] / max(||x[i,:]||, eps)  (the per-vector clamp of torch.cosine_similarity,
+ * training.py:297-299, eps = 1e-8).  In place allowed (y == x).  y_bf16 nullable: bf16 copy. */
+int tt_l2_normalize_rows(const float* x, int64_t N, int P, float eps, float* y, void* y_bf16,
+                         tt_stream_t stream);
+
+/* Exhaustive corpus scan: for every query the k best documents of this shard by dot product of
+ * the (already normalised) rows, ties broken by ascending id.  The score matrix is never stored.
+ *   Qn [Q,P] f32, Dn [N,P] f32 (TT_PREC_FP32) — or bf16 copies Qb/Db for the tensor-core scan, in
+ *   which case the fp32 arrays are still used to re-score the k_cand best candidates exactly.
+ *   id_base: global id of local document 0 (corpus sharding, one shard per GPU).
+ *   top_score [Q,k] f32 descending; top_id [Q,k] i64 (-1 where fewer than k docs exist).
+ *   ws: tt_scan_ws_bytes(Q,N,P,k,precision) bytes. */
+size_t tt_scan_ws_bytes(int Q, int64_t N, int P, int k, int precision);
+int tt_scan_topk(const float* Qn, const float* Dn, const void* Qb, const void* Db, int Q, int64_t N,
+                 int P, int k, int64_t id_base, int precision, float* top_score, int64_t* top_id,
+                 void* ws, size_t ws_bytes, tt_stream_t stream);
+
+/* Exact fp32 scores of per-query candidate lists (validation mode of evaluate_model,
+ * training.py:253-267,288-299): cand [Q,C] i64 local doc indices (-1 = padding).
+ * Writes the k best per query (score desc, id asc). */
+int tt_score_candidates(const float* Qn, const float* Dn, const int64_t* cand, int Q, int C, int P,
+                        int k, int64_t id_base, float* top_score, int64_t* top_id,
+                        tt_stream_t stream);
+
+/* Merge G partial top-k lists per query (corpus shards after the all-gather):
+ * parts_score/parts_id [G,Q,k] -> [Q,k], order (score desc, id asc), ids < 0 ignored. */
+int tt_topk_merge(const float* parts_score, const int64_t* parts_id, int G, int Q, int k,
+                  float* top_score, int64_t* top_id, tt_stream_t stream);
+
+/* NDCG@k of binary relevance from top-k ids (sklearn.metrics.ndcg_score semantics used at
+ * training.py:304-309, tie-free case): rel_offsets [Q+1] / rel_ids (CSR, global ids, each list
+ * sorted ascending), ndcg [Q] f64.  IDCG = sum_{r<min(R,k)} 1/log2(r+2); ndcg = 0 when R == 0.
+ * kk <= k evaluates NDCG@kk from the first kk entries. */
+int tt_ndcg_at_k(const int64_t* top_id, int Q, int k, int kk, const int64_t* rel_offsets,
+                 const int64_t* rel_ids, double* ndcg, tt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H */
