@@ -100,7 +100,7 @@ int tt_pool_bwd(const float* dxhat, const float* xhat, const float* cnt, const f
 /* ------------------------------------------------------------------------------------------
  * Projection MLP of one tower: y = relu(x W1^T + b1) W2^T + b2      (model.py:33-38,59)
  *   x [M,H]; W1 [P,H]; b1 [P]; W2 [P,P]; b2 [P]; h [M,P] (post-ReLU, saved for backward); y [M,P].
- *   ws: scratch of tt_mlp_ws_bytes(M,H,P,precision) bytes (0 for TT_PREC_FP32).
+ *   ws: scratch of tt_mlp_ws_bytes(M,H,P,precision) bytes.
  * ---------------------------------------------------------------------------------------- */
 size_t tt_mlp_ws_bytes(int M, int H, int P, int precision);
 int tt_encode_fwd(const float* x, int M, int H, int P, const float* W1, const float* b1,
@@ -167,6 +167,14 @@ int tt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                  tt_stream_t stream);
 
+/* Graph-capturable variant: the step count and beta powers live in device memory
+ * (state: 4 doubles {t, beta1^t, beta2^t, unused}, zero-initialised = "no step taken yet" — a zeroed
+ * state is advanced to t=1 by the first call), so replaying a captured graph advances the bias
+ * correction without any host-side argument change. */
+int tt_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                     float lr, float beta1, float beta2, float eps, double* state, float grad_scale,
+                     tt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Retrieval / evaluation (training.py:244-311 restated as a batched exhaustive scan).
  * ---------------------------------------------------------------------------------------- */
@@ -192,6 +200,7 @@ int tt_scan_topk(const float* Qn, const float* Dn, const void* Qb, const void* D
  * Writes the k best per query (score desc, id asc). */
 int tt_score_candidates(const float* Qn, const float* Dn, const int64_t* cand, int Q, int C, int P,
                         int k, int64_t id_base, float* top_score, int64_t* top_id,
+                        float* all_scores /* [Q,C] nullable: every candidate's score */,
                         tt_stream_t stream);
 
 /* Merge G partial top-k lists per query (corpus shards after the all-gather):

@@ -1,0 +1,36 @@
+// tcgen05 / TMA (sm_100a) paths: projection GEMMs with fused epilogues and the tensor-core corpus scan.
+#pragma once
+#include "tt_common.cuh"
+#include "tt_pool.cuh"
+
+namespace tt {
+
+size_t mlp_sm100_ws_bytes(int M, int H, int P);
+int mlp_fwd_sm100(const float* x, int M, int H, int P, const float* W1, const float* b1, const float* W2,
+                  const float* b2, float* h, float* y, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+int mlp_bwd_sm100(const float* dy, const float* x, const float* h, const float* W1, const float* W2, int M, int H,
+                  int P, float* dW1, float* db1, float* dW2, float* db2, float* dx, int accumulate, int precision,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+
+struct StepSm100 {
+  PoolParams pool;  // xhat/cnt/nrm/err filled by the caller; split outputs filled by step_sm100
+  int table_dtype;
+  int B, H, P;
+  const float *Wq1, *bq1, *Wq2, *bq2, *Wd1, *bd1, *Wd2, *bd2;
+  float margin, inv_batch, grad_scale;
+  float* loss;
+  float *dWq1, *dbq1, *dWq2, *dbq2, *dWd1, *dbd1, *dWd2, *dbd2;
+  float *h, *y, *stats, *dy;  // fp32 activations [3B,P] / [B,8]
+  float* dxhat;               // [3B,H] nullable
+  int n_split;                // 3 = bf16x3, 1 = bf16
+  void* ws;
+  size_t ws_bytes;
+};
+size_t step_sm100_ws_bytes(int B, int H, int P, int train_table);
+int step_sm100(const StepSm100& s, cudaStream_t st);
+
+size_t scan_sm100_ws_bytes(int Q, long long N, int P, int k);
+int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void* Db, int Q, long long N, int P, int k,
+                    long long id_base, float* top_score, long long* top_id, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace tt

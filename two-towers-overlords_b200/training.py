@@ -1,0 +1,560 @@
+"""
+Training / evaluation for the two-towers model — B200-native drop-in for the reference's
+backend/training.py: `clear_gpu_memory`, `train_epoch`, `train_epoch_optimized`, `evaluate_model`,
+`run_training` keep the reference's signatures, return values and printed/logged keys, so backend/main.py
+runs on top unchanged.
+
+Additions (the B200 path proper):
+  * FusedTrainer      one tt_triplet_step (pooled gather -> both tower MLPs -> loss -> all gradients) + one
+                      fused Adam launch per step, captured in a CUDA graph; data-parallel with ONE NCCL
+                      all-reduce of the flat gradient buffer (+ the loss in its last slot) per step.
+  * evaluate_model    scores every query against the candidate documents with the corpus-scan / candidate
+                      kernels and computes NDCG@k on the device; only tie cases that the closed form cannot
+                      express fall back to the exact tie-averaged formula.
+"""
+from __future__ import annotations
+
+import math
+import random
+from typing import Optional, Union
+
+import numpy as np
+import torch
+from torch import GradScaler, autocast
+
+try:
+    from . import ops
+    from .data import MSMarcoDataset, TokenTripletLoader, TripletDataLoader
+    from .model import TokenBatch, TripletLoss, TwoTowersModel
+except ImportError:
+    import ops
+    from data import MSMarcoDataset, TokenTripletLoader, TripletDataLoader
+    from model import TokenBatch, TripletLoss, TwoTowersModel
+
+try:  # wandb is optional at import time; only touched when logging is requested
+    import wandb
+except Exception:  # noqa: BLE001
+    wandb = None
+
+
+def clear_gpu_memory():
+    """Clear GPU memory cache to reduce fragmentation (training.py:19-23)."""
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------------
+# reference-shaped epoch loops (training.py:26-133)
+# --------------------------------------------------------------------------------------------------
+def train_epoch(model, dataloader, criterion, optimizer, log_wandb: bool = True) -> float:
+    """Train for one epoch (training.py:26-63).  The per-batch loss stays on the device; the host only
+    reads it where the reference prints/logs it."""
+    total_loss = None
+    num_batches = 0
+    for queries, positives, negatives in dataloader:
+        optimizer.zero_grad()
+        query_embeds = model.encode_queries(queries)
+        positive_embeds = model.encode_documents(positives)
+        negative_embeds = model.encode_documents(negatives)
+        loss = criterion(query_embeds, positive_embeds, negative_embeds)
+        loss.backward()
+        optimizer.step()
+        total_loss = loss.detach().double() if total_loss is None else total_loss + loss.detach().double()
+        num_batches += 1
+        if log_wandb and wandb is not None:
+            wandb.log({"batch_loss": loss.item(), "batch": num_batches})
+        if num_batches % 10 == 0:
+            print(f"Batch {num_batches}, Loss: {loss.item():.4f}")
+    if num_batches == 0:
+        raise ZeroDivisionError("train_epoch: empty dataloader")
+    return float(total_loss.item()) / num_batches
+
+
+def train_epoch_optimized(model, dataloader, criterion, optimizer, device, scaler, accumulation_steps: int = 2,
+                          log_wandb: bool = True) -> float:
+    """Mixed-precision + gradient-accumulation epoch (training.py:66-133).  The kernels compute in fp32 /
+    split-bf16 regardless of autocast, so the GradScaler only ever sees finite fp32 gradients; its
+    scale/unscale protocol is kept so that the optimiser-step cadence matches the reference."""
+    model.train()
+    total_loss = None
+    num_batches = 0
+    for batch_idx, (queries, positives, negatives) in enumerate(dataloader):
+        with autocast(device.type):
+            query_embeds = model.encode_queries(queries)
+            positive_embeds = model.encode_documents(positives)
+            negative_embeds = model.encode_documents(negatives)
+            loss = criterion(query_embeds, positive_embeds, negative_embeds)
+            loss = loss / accumulation_steps
+        scaler.scale(loss).backward()
+        if (batch_idx + 1) % accumulation_steps == 0:
+            scaler.step(optimizer)
+            scaler.update()
+            optimizer.zero_grad()
+        unscaled = loss.detach().double() * accumulation_steps
+        total_loss = unscaled if total_loss is None else total_loss + unscaled
+        num_batches += 1
+        if log_wandb and wandb is not None and batch_idx % 10 == 0:
+            wandb.log({
+                "batch_loss": loss.item() * accumulation_steps,
+                "batch": num_batches,
+                "gpu_memory_allocated": torch.cuda.memory_allocated() / 1e9 if torch.cuda.is_available() else 0,
+                "gpu_memory_reserved": torch.cuda.memory_reserved() / 1e9 if torch.cuda.is_available() else 0,
+            })
+        if batch_idx % 10 == 0:
+            print(f"Batch {batch_idx}, Loss: {loss.item() * accumulation_steps:.4f}")
+    if num_batches == 0:
+        raise ZeroDivisionError("train_epoch_optimized: empty dataloader")
+    return float(total_loss.item()) / num_batches
+
+
+# --------------------------------------------------------------------------------------------------
+# fused B200 trainer
+# --------------------------------------------------------------------------------------------------
+class FusedTrainer:
+    """Whole training step (training.py:37-51) as: H2D token copy -> tt_triplet_step -> [NCCL all-reduce]
+    -> tt_adam_step_dev, on static buffers so the device part replays as one CUDA graph.
+
+    The 8 projection tensors are re-pointed at views of one flat fp32 buffer, so the model's
+    `state_dict()` / `parameters()` always see the trained values; gradients live in a second flat buffer
+    whose last element carries the loss (one all-reduce covers both)."""
+
+    def __init__(self, model: TwoTowersModel, margin: float, lr: float, batch_size: int, Lq: int = 32, Ld: int = 256,
+                 precision: Optional[str] = None, world_size: int = 1, rank: int = 0, use_graph: bool = True,
+                 betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, ids_dtype=torch.int32,
+                 mask_dtype=torch.uint8):
+        qt, dt = model.query_tower, model.document_tower
+        self.model = model
+        self.device = qt.pretrained_model.device
+        if self.device.type != "cuda":
+            raise RuntimeError("FusedTrainer needs the model on a CUDA device (no CPU fallback)")
+        self.B, self.Lq, self.Ld = batch_size, Lq, Ld
+        self.H = qt.embedding_dim
+        self.P = qt.projection[0].out_features
+        self.vocab = qt.pretrained_model.config.vocab_size
+        self.margin, self.lr, self.betas, self.eps = float(margin), float(lr), betas, float(eps)
+        self.world, self.rank, self.pg = world_size, rank, process_group
+        self.precision = precision or qt.precision
+        self.train_table = bool(qt.pretrained_model.table.requires_grad)
+        params = model.projection_parameters()
+        sizes = [p.numel() for p in params]
+        self.n_param = sum(sizes)
+        dev = self.device
+        self.flat_p = torch.empty(self.n_param, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.n_param + 1, dtype=torch.float32, device=dev)  # [+1]: loss
+        self.exp_avg = torch.zeros(self.n_param, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n_param, dtype=torch.float32, device=dev)
+        self.adam_state = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.p_views, self.g_views = [], []
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(params, sizes):
+                view = self.flat_p[off: off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view  # the nn.Parameter now aliases the flat buffer
+                self.p_views.append(view)
+                self.g_views.append(self.flat_g[off: off + n].view_as(p))
+                off += n
+        self.loss_view = self.flat_g[self.n_param:]
+        # static token buffers (graph replays read these addresses)
+        mk = lambda L, dt_: torch.zeros(batch_size, L, dtype=dt_, device=dev)  # noqa: E731
+        self.tok = (mk(Lq, ids_dtype), mk(Lq, mask_dtype), mk(Ld, ids_dtype), mk(Ld, mask_dtype),
+                    mk(Ld, ids_dtype), mk(Ld, mask_dtype))
+        self.table_grads = None
+        if self.train_table:
+            self.table_grads = (torch.zeros_like(qt.pretrained_model.table, dtype=torch.float32),
+                                torch.zeros_like(dt.pretrained_model.table, dtype=torch.float32))
+        self.step_obj = ops.TripletStep(batch_size, Lq, Ld, self.H, self.P, self.vocab, self.precision, dev,
+                                        train_table=self.train_table)
+        self.step_obj.loss = self.loss_view  # loss lands in the flat gradient buffer's last slot
+        self.step_obj.bind(self.tok, (qt.pretrained_model.table.data, dt.pretrained_model.table.data), self.p_views,
+                           self.g_views, self.margin, 1.0 / (batch_size * world_size), 1.0, self.table_grads)
+        self.use_graph = use_graph
+        self.graph_fb = self.graph_opt = None
+        self.steps_done = 0
+        self.kernel_launches_per_step = None
+
+    # -- pieces ------------------------------------------------------------------------------------
+    def load_tokens(self, q: TokenBatch, p: TokenBatch, n: TokenBatch):
+        """Host (pinned) or device token batches -> static device buffers, async on the current stream."""
+        for dst, src in zip(self.tok, (q.input_ids, q.attention_mask, p.input_ids, p.attention_mask,
+                                        n.input_ids, n.attention_mask)):
+            dst.copy_(src, non_blocking=True)
+
+    def _fwd_bwd(self):
+        self.step_obj.run()
+
+    def _optimizer(self):
+        b1, b2 = self.betas
+        N = ops.N
+        N.check(N.load().tt_adam_step_dev(N.ptr(self.flat_p), N.ptr(self.flat_g), N.ptr(self.exp_avg),
+                                          N.ptr(self.exp_avg_sq), self.n_param, self.lr, b1, b2, self.eps,
+                                          N.ptr(self.adam_state), 1.0, N.stream()), "tt_adam_step_dev")
+        # (table training uses a plain SGD-free path: the caller owns the table optimiser)
+
+    def _capture(self):
+        # warm up on a side stream as torch requires, then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self._fwd_bwd()
+            if self.world == 1:
+                self._optimizer()
+        if self.world > 1:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self._optimizer()
+
+    def step(self) -> torch.Tensor:
+        """One optimiser step on the tokens currently in the static buffers; returns the (global) loss as
+        a device scalar — no host sync."""
+        if self.use_graph:
+            if self.graph_fb is None:
+                self._capture()  # warm-up runs forward/backward only, capture itself executes nothing
+            self.graph_fb.replay()
+            if self.world > 1:
+                torch.distributed.all_reduce(self.flat_g, group=self.pg)
+                self.graph_opt.replay()
+        else:
+            self._fwd_bwd()
+            if self.world > 1:
+                torch.distributed.all_reduce(self.flat_g, group=self.pg)
+            self._optimizer()
+        self.steps_done += 1
+        return self.loss_view[0]
+
+    def train_epoch(self, loader: TokenTripletLoader, log_every: int = 0) -> float:
+        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        nb = 0
+        for q, p, n in loader:
+            self.load_tokens(q, p, n)
+            loss = self.step()
+            total += loss.double()
+            nb += 1
+            if log_every and nb % log_every == 0:
+                print(f"Batch {nb}, Loss: {loss.item():.4f}")
+        if nb == 0:
+            raise ZeroDivisionError("FusedTrainer.train_epoch: empty loader")
+        return float(total.item()) / nb
+
+
+# --------------------------------------------------------------------------------------------------
+# evaluation (training.py:136-380)
+# --------------------------------------------------------------------------------------------------
+_K_SCAN = 16  # candidates kept per query (>= 10) so ties at the top-10 boundary are visible
+
+
+def _tie_averaged_ndcg(rel: np.ndarray, score: np.ndarray, k: int) -> float:
+    """sklearn.metrics.ndcg_score semantics for one query (default ignore_ties=False), used only when a
+    tie reaches past the scanned candidates.  Tie groups share the mean gain of their ranks."""
+    n = len(rel)
+    disc = 1.0 / np.log2(np.arange(n) + 2.0)
+    disc[k:] = 0.0
+    order = np.argsort(-score, kind="stable")
+    s_sorted, r_sorted = score[order], rel[order].astype(np.float64)
+    dcg, i = 0.0, 0
+    while i < n and i < k:
+        j = i
+        while j + 1 < n and s_sorted[j + 1] == s_sorted[i]:
+            j += 1
+        dcg += r_sorted[i: j + 1].mean() * disc[i: j + 1].sum()
+        i = j + 1
+    ideal = float((np.sort(rel)[::-1].astype(np.float64) * disc).sum())
+    return 0.0 if ideal == 0 else dcg / ideal
+
+
+def _ndcg_from_lists(top_s: np.ndarray, top_i: np.ndarray, relevant: set, n_rel_in_pool: int, k: int,
+                     exact_fallback) -> float:
+    """NDCG@k of one query from its best _K_SCAN (score,id) pairs; tie groups inside the list are averaged
+    exactly; a tie group that runs off the end of the list triggers `exact_fallback()`."""
+    m = int((top_i >= 0).sum())
+    if m > k and top_s[m - 1] == top_s[k - 1] and m == len(top_i):
+        return exact_fallback()
+    gains = np.array([1.0 if int(d) in relevant else 0.0 for d in top_i[:m]])
+    disc = np.zeros(m)
+    disc[: min(k, m)] = 1.0 / np.log2(np.arange(min(k, m)) + 2.0)
+    dcg, i = 0.0, 0
+    while i < m and i < k:
+        j = i
+        while j + 1 < m and top_s[j + 1] == top_s[i]:
+            j += 1
+        dcg += gains[i: j + 1].mean() * disc[i: j + 1].sum()
+        i = j + 1
+    idcg = float((1.0 / np.log2(np.arange(min(n_rel_in_pool, k)) + 2.0)).sum())
+    return 0.0 if idcg == 0 else dcg / idcg
+
+
+def evaluate_model(
+    model: TwoTowersModel,
+    dataset,
+    sample_size: int = 200,
+    min_query_groups: int = 20,
+    candidate_pool_size: int = 100,
+    comprehensive: bool = False,
+    log_wandb: bool = False,
+    wandb_prefix: str = "final_",
+    batch_size: int = 1024,
+) -> Union[float, dict[str, float]]:
+    """NDCG evaluation with all relevant documents per query (training.py:136-380): same sampling, same
+    candidate pools, same metrics and return type; scoring is one batched device pass instead of a per-query
+    CPU cosine + sklearn call."""
+    print(f"Sampling documents for evaluation (initial sample size: {sample_size})...")
+    model.eval()
+    clear_gpu_memory()
+
+    # group by query_id until enough unique queries (training.py:184-201; same `random` call sequence)
+    query_groups: dict[int, dict] = {}
+    sample_multiplier = 1
+    print(f"Grouping data by queries (target: {min_query_groups} unique queries)...")
+    while len(query_groups) < min_query_groups and sample_multiplier <= 10:
+        sample_size_current = min(sample_size * sample_multiplier, len(dataset))
+        for i in random.sample(range(len(dataset)), sample_size_current):
+            item = dataset[i]
+            group = query_groups.setdefault(item["query_id"], {"query": item["query"], "relevant_docs": {}})
+            group["relevant_docs"].setdefault(item["positive"], None)  # insertion-ordered set
+        sample_multiplier += 1
+    query_ids = sorted(query_groups, key=lambda qid: len(query_groups[qid]["relevant_docs"]), reverse=True)
+    query_ids = query_ids[:min_query_groups]
+    if not query_ids:
+        raise ZeroDivisionError("evaluate_model: no queries to evaluate")
+    total_relevant_docs = sum(len(query_groups[q]["relevant_docs"]) for q in query_ids)
+    avg_relevant_per_query = total_relevant_docs / len(query_ids)
+    print(f"Selected {len(query_ids)} queries for evaluation")
+    print(f"  Total relevant documents across these queries: {total_relevant_docs}")
+    print(f"  Average relevant docs per query: {avg_relevant_per_query:.2f}")
+
+    # document universe and per-query candidate lists
+    full_pool = candidate_pool_size == -1
+    if full_pool:
+        print("🚀 Pre-encoding *all* documents for efficiency (this may take a moment)...")
+        universe = list(dataset.get_unique_passages())
+    else:
+        universe = list(dict.fromkeys(d for q in query_ids for d in query_groups[q]["relevant_docs"]))
+    doc_index = {d: i for i, d in enumerate(universe)}
+    if len(universe) <= 1:
+        raise ValueError("Computing NDCG is only meaningful when there is more than 1 document.")
+    cand_lists = None
+    if not full_pool:
+        cand_lists = []
+        for q in query_ids:
+            rel = query_groups[q]["relevant_docs"]
+            # irrelevant = every other selected query's relevant docs (training.py:255-261); sorted so a
+            # seeded run is reproducible (the reference's order depends on PYTHONHASHSEED)
+            irrelevant = sorted({d for o in query_ids if o != q for d in query_groups[o]["relevant_docs"] if d not in rel})
+            if len(irrelevant) > candidate_pool_size:
+                irrelevant = random.sample(irrelevant, candidate_pool_size)
+            cand_lists.append([doc_index[d] for d in rel] + [doc_index[d] for d in irrelevant])
+            if len(cand_lists[-1]) <= 1:
+                raise ValueError("Computing NDCG is only meaningful when there is more than 1 document.")
+
+    with torch.no_grad():
+        doc_embeds = model.encode_documents_batched(universe, batch_size=batch_size)
+        query_embeds = model.encode_queries([query_groups[q]["query"] for q in query_ids])
+        if full_pool:
+            print(f"🔥 Pre-encoded {len(universe)} documents to reuse for all queries")
+        dev = doc_embeds.device
+        Dn = ops.l2_normalize_rows(doc_embeds)  # per-vector clamp of torch.cosine_similarity (training.py:297)
+        Qn = ops.l2_normalize_rows(query_embeds)
+        if full_pool:
+            kk = min(_K_SCAN, len(universe))
+            top_s, top_i = ops.scan_topk(Qn, Dn, k=kk, precision="fp32")
+            pool_sizes = [len(universe)] * len(query_ids)
+        else:
+            C = max(len(c) for c in cand_lists)
+            cand = torch.full((len(cand_lists), C), -1, dtype=torch.int64)
+            for r, c in enumerate(cand_lists):
+                cand[r, : len(c)] = torch.tensor(c, dtype=torch.int64)
+            cand = cand.to(dev)
+            kk = min(_K_SCAN, C)
+            top_s, top_i = ops.score_candidates(Qn, Dn, cand, k=kk)
+            pool_sizes = [len(c) for c in cand_lists]
+        # NDCG on the device (tie-free closed form) ...
+        rel_lists = [sorted(doc_index[d] for d in query_groups[q]["relevant_docs"] if d in doc_index) for q in query_ids]
+        offs = torch.tensor(np.concatenate([[0], np.cumsum([len(r) for r in rel_lists])]), dtype=torch.int64, device=dev)
+        rel_flat = torch.tensor([d for r in rel_lists for d in r], dtype=torch.int64, device=dev)
+        ks = (10, 5, 1) if comprehensive else (10,)
+        dev_ndcg = {k: ops.ndcg_at_k(top_i, offs, rel_flat, kk=min(k, kk)).cpu().numpy() for k in ks}
+        top_s_h, top_i_h = top_s.cpu().numpy(), top_i.cpu().numpy()
+
+    # ... and exact tie handling for the (rare) queries whose best scores tie past the scanned list
+    def exact(qi: int, k: int) -> float:
+        idx = np.arange(len(universe)) if full_pool else np.array(cand_lists[qi])
+        sc = ops.candidate_scores(Qn[qi: qi + 1], Dn, idx)
+        rel_set_q = set(rel_lists[qi])
+        rel = np.array([1 if int(d) in rel_set_q else 0 for d in idx])
+        return _tie_averaged_ndcg(rel, sc, k)
+
+    scores = {k: [] for k in ks}
+    for qi in range(len(query_ids)):
+        m = int((top_i_h[qi] >= 0).sum())
+        has_tie = bool((np.diff(top_s_h[qi][:m]) == 0).any()) if m > 1 else False
+        rel_set = set(rel_lists[qi])
+        n_rel = len(rel_set)
+        for k in ks:
+            if not has_tie:
+                scores[k].append(float(dev_ndcg[k][qi]))
+            else:
+                scores[k].append(_ndcg_from_lists(top_s_h[qi], top_i_h[qi], rel_set, n_rel, k,
+                                                  lambda qi=qi, k=k: exact(qi, k)))
+        if qi == 0:
+            print("\nSample evaluation results:")
+            print(f"Query: {query_groups[query_ids[0]]['query']}")
+            print(f"Number of relevant docs: {len(rel_set)}")
+            print(f"Number of candidate docs: {pool_sizes[0]}")
+            print(f"NDCG@10 score for this query: {scores[10][0]:.4f}")
+            print("Top 10 ranked documents:")
+            for rank, d in enumerate(top_i_h[0][:10]):
+                if d < 0:
+                    break
+                tag = "RELEVANT" if int(d) in rel_set else "irrelevant"
+                text = str(universe[int(d)])
+                print(f"  {rank + 1}. [{tag}] {text[:100] + '...' if len(text) > 100 else text}")
+
+    mean_ndcg_10 = float(np.mean(scores[10]))
+    if not comprehensive:
+        print(f"\nMean NDCG@10 across {len(query_ids)} queries: {mean_ndcg_10:.4f}")
+        return mean_ndcg_10
+    results = {
+        f"{wandb_prefix}ndcg_10": mean_ndcg_10,
+        f"{wandb_prefix}ndcg_5": float(np.mean(scores[5])),
+        f"{wandb_prefix}ndcg_1": float(np.mean(scores[1])),
+        f"{wandb_prefix}ndcg_10_std": float(np.std(scores[10])),
+        f"{wandb_prefix}queries_evaluated": len(query_ids),
+        f"{wandb_prefix}total_relevant_docs": total_relevant_docs,
+        f"{wandb_prefix}avg_relevant_per_query": avg_relevant_per_query,
+    }
+    print("\n" + "=" * 60)
+    print("COMPREHENSIVE EVALUATION RESULTS")
+    print("=" * 60)
+    print("📊 Performance Metrics:")
+    print(f"   NDCG@1:  {results[f'{wandb_prefix}ndcg_1']:.4f}")
+    print(f"   NDCG@5:  {results[f'{wandb_prefix}ndcg_5']:.4f}")
+    print(f"   NDCG@10: {results[f'{wandb_prefix}ndcg_10']:.4f} (±{results[f'{wandb_prefix}ndcg_10_std']:.4f})")
+    print("\n📈 Evaluation Set Coverage:")
+    print(f"   Queries evaluated: {results[f'{wandb_prefix}queries_evaluated']}")
+    print(f"   Total relevant documents: {results[f'{wandb_prefix}total_relevant_docs']}")
+    print(f"   Avg relevant docs/query: {results[f'{wandb_prefix}avg_relevant_per_query']:.2f}")
+    if log_wandb and wandb is not None:
+        wandb.log(results)
+        print("\n✅ Comprehensive test results logged to wandb")
+    return results
+
+
+# --------------------------------------------------------------------------------------------------
+# run driver (training.py:383-529)
+# --------------------------------------------------------------------------------------------------
+def run_training(
+    num_epochs: int = 3,
+    batch_size: int = 1024,
+    learning_rate: float = 1e-4,
+    max_samples: int = 10000,
+    projection_dim: int = 128,
+    margin: float = 0.1,
+    project_name: str = "two-towers-retrieval",
+    use_wandb: bool = True,
+    wandb_config: Optional[dict] = None,
+    accumulation_steps: int = 2,
+    use_mixed_precision: bool = True,
+    num_workers: int = 4,
+    run_comprehensive_test: bool = True,
+    fused: Optional[bool] = None,
+    table_dtype: torch.dtype = torch.float32,
+) -> TwoTowersModel:
+    """Main training function (training.py:383-529).  `fused` (additive) selects the FusedTrainer; by
+    default it is used whenever the dataset is token-bank backed and no gradient accumulation / wandb
+    gradient hooks require the reference-shaped loop."""
+    print("Initializing model and data...")
+    if not torch.cuda.is_available():
+        raise RuntimeError("two-towers-overlords_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+    device = torch.device("cuda")
+    print(f"Using device: {device}")
+    print(f"GPU: {torch.cuda.get_device_name(0)}")
+    print(f"Memory: {torch.cuda.get_device_properties(0).total_memory / 1e9:.1f}GB")
+
+    use_wandb = bool(use_wandb and wandb is not None)
+    if use_wandb:
+        config = {
+            "epochs": num_epochs, "batch_size": batch_size, "learning_rate": learning_rate,
+            "max_samples": max_samples, "model_name": "sentence-transformers/all-MiniLM-L6-v2",
+            "loss_function": "triplet_loss", "distance_metric": "cosine", "margin": margin,
+            "dataset_type": "ms_marco_all_passages", "device": str(device),
+            "device_name": torch.cuda.get_device_name(0),
+        }
+        if wandb_config:
+            config.update(wandb_config)
+        if not wandb.run:
+            wandb.init(project=project_name, config=config)
+
+    model = TwoTowersModel(projection_dim=projection_dim, table_dtype=table_dtype).to(device)
+    criterion = TripletLoss(margin=margin)
+    optimizer = torch.optim.Adam(model.parameters(), lr=learning_rate)
+    if use_wandb:
+        wandb.watch(model, log="all", log_freq=100)
+        wandb.log({"total_parameters": sum(p.numel() for p in model.parameters())})
+
+    train_ds = MSMarcoDataset("train", max_samples=max_samples)
+    val_ds = MSMarcoDataset("validation", max_samples=1000)
+
+    def use_bank_tokenizer(ds, *more):
+        tok = ds.tokenizer() if hasattr(ds, "tokenizer") else None
+        if tok is not None:
+            for d in more:
+                tok.banks.update(d.tokenizer().banks)
+            model.query_tower.tokenizer = model.document_tower.tokenizer = tok
+        return tok
+
+    bank_backed = use_bank_tokenizer(train_ds, val_ds) is not None
+    train_dl = TripletDataLoader(train_ds, batch_size=batch_size, num_workers=num_workers, device=device)
+    if fused is None:
+        fused = bank_backed and accumulation_steps == 1 and not use_wandb
+
+    print("Training configuration:")
+    print(f"  Physical batch size: {batch_size}")
+    print(f"  Gradient accumulation steps: {accumulation_steps}")
+    print(f"  Effective batch size: {batch_size * accumulation_steps}")
+    print(f"  Mixed precision: {use_mixed_precision}")
+    print(f"  DataLoader workers: {num_workers}")
+    print(f"  Fused B200 step: {fused}")
+
+    scaler = GradScaler(device.type) if use_mixed_precision else None
+    trainer = token_dl = None
+    if fused:
+        trainer = FusedTrainer(model, margin, learning_rate, batch_size)
+        token_dl = TokenTripletLoader(train_ds, batch_size, trainer.Lq, trainer.Ld)
+
+    print(f"Starting training for {num_epochs} epochs...")
+    for epoch in range(num_epochs):
+        print(f"\nEpoch {epoch + 1}/{num_epochs}")
+        if trainer is not None:
+            avg_loss = trainer.train_epoch(token_dl, log_every=10)
+        elif use_mixed_precision and scaler is not None:
+            avg_loss = train_epoch_optimized(model=model, dataloader=train_dl, criterion=criterion,
+                                             optimizer=optimizer, device=device, scaler=scaler,
+                                             accumulation_steps=accumulation_steps, log_wandb=use_wandb)
+        else:
+            avg_loss = train_epoch(model, train_dl, criterion, optimizer, log_wandb=use_wandb)
+        print(f"Average training loss: {avg_loss:.4f}")
+        ndcg = evaluate_model(model, val_ds, batch_size=batch_size)
+        print(f"Validation NDCG@10: {ndcg:.4f}")
+        if use_wandb:
+            wandb.log({"epoch": epoch + 1, "avg_train_loss": avg_loss, "val_ndcg_10": ndcg})
+
+    print("\n" + "=" * 60)
+    if run_comprehensive_test:
+        print("TRAINING COMPLETED - Starting comprehensive testing")
+        print("=" * 60)
+        test_dataset = MSMarcoDataset("test", max_samples=10_000)
+        use_bank_tokenizer(train_ds, val_ds, test_dataset)
+        _ = evaluate_model(model=model, dataset=test_dataset, min_query_groups=200, candidate_pool_size=-1,
+                           comprehensive=True, log_wandb=use_wandb, batch_size=batch_size)
+    else:
+        print("TRAINING COMPLETED - Skipping comprehensive testing")
+        print("=" * 60)
+    if use_wandb:
+        wandb.finish()
+    return model
