@@ -32,8 +32,13 @@ def rel_err(got: torch.Tensor, want: torch.Tensor) -> float:
 
 
 def max_rel(got, want, floor):
+    """Largest row-wise relative error: max_rows ||got - want||_inf / max(||want||_inf, floor)."""
     got, want = got.detach().double().cpu(), want.detach().double().cpu()
-    return float(((got - want).abs() / want.abs().clamp_min(floor)).max())
+    if got.dim() == 1:
+        got, want = got[None], want[None]
+    num = (got - want).abs().amax(dim=-1)
+    den = want.abs().amax(dim=-1).clamp_min(floor)
+    return float((num / den).max())
 
 
 # ---------------------------------------------------------------------------------------------------
