@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""
+bench.py — the two-tower hot path on B200: train triplets/s (headline) with the pooled-gather roofline, an
+end-to-end number through the public API with host buffers, a top-10 corpus-scan figure, and the CPU
+baseline (the oracle port of the reference's fp32 step, oracle/two_towers_oracle.py) beside it.
+
+    python bench.py [--gpus N --steps K --warmup W]            # N>1: launched by torch.distributed.run
+    python bench.py --impl reference [--steps K --warmup W]    # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1], "heavy GPU run shape"): per-GPU batch 2048 triplets, projection dim 512,
+margin 0.3, query length 32 / document length 256 tokens (SURVEY.md §8d shape U: full-length rows, ids
+uniform in [999, 30522) — the roofline case), random-init 30522x384 tables, Adam lr 1e-3.  Weak scaling:
+every rank processes its own 2048-triplet batch, one NCCL all-reduce of the flat projection gradient per step.
+
+A "step" = H2D'd tokens -> pooled gather (q,p,n) -> both tower MLPs -> cosine triplet loss -> all gradients
+-> [all-reduce] -> Adam.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU, P_DIM, LQ, LD, MARGIN, LR = 2048, 512, 32, 256, 0.3, 1e-3
+VOCAB, HIDDEN = 30522, 384
+N_TOKEN_SETS = 32  # rotating input batches: 32 x 5.57 MB = 178 MB > 126 MB L2
+METRIC, UNIT = "train_triplets_per_sec", "triplets/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, 1590.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic inputs (same generator for both arms)
+# --------------------------------------------------------------------------------------------------
+def token_sets(n_sets: int, B: int, seed: int, ids_dtype, mask_dtype, pin: bool):
+    """n_sets x (q_ids,q_mask,p_ids,p_mask,n_ids,n_mask): shape U, negatives = in-batch derangement of the positives."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_sets):
+        q = torch.randint(999, VOCAB, (B, LQ), generator=g, dtype=torch.int64)
+        p = torch.randint(999, VOCAB, (B, LD), generator=g, dtype=torch.int64)
+        shift = int(torch.randint(1, B, (1,), generator=g)) if B > 1 else 0
+        n = torch.roll(p, shift, 0)  # negative_i = positive_{i-shift}: no fixed point
+        ts = []
+        for ids in (q, p, n):
+            ts += [ids.to(ids_dtype), torch.ones(ids.shape, dtype=mask_dtype)]
+        if pin:
+            ts = [t.pin_memory() for t in ts]
+        out.append(tuple(ts))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thr = [], None, None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                 str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 - 0.06 <= t <= t1 + 0.06 and len(r) >= 7] or \
+               [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return None
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's fp32 training step restated in oracle/ (training.py:36-53)
+# --------------------------------------------------------------------------------------------------
+def cpu_train_throughput(budget_s: float, steps: int | None = None, warmup: int = 1, batch: int | None = None):
+    """Times oracle.train_step on the host cores.  Returns (triplets/s, description dict)."""
+    from oracle import two_towers_oracle as O
+
+    torch.manual_seed(0)
+    threads = torch.get_num_threads()
+    model = O.OracleTwoTowers(P_DIM, vocab=VOCAB, hidden=HIDDEN)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    B = batch or B_PER_GPU
+    sets = token_sets(2, B, 1234, torch.int64, torch.int64, pin=False)
+    t0 = time.perf_counter()
+    O.train_step(model, opt, sets[0], MARGIN)
+    t_first = time.perf_counter() - t0
+    for _ in range(max(0, warmup - 1)):
+        O.train_step(model, opt, sets[1], MARGIN)
+    if steps is None:
+        steps = max(2, min(16, int(budget_s / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.train_step(model, opt, sets[i % 2], MARGIN)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, {"cores": threads, "steps": steps, "batch": B, "seconds": round(dt, 2),
+                            "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # size the per-step sample so that K steps end within ~2 minutes
+    probe, info = cpu_train_throughput(0, steps=1, warmup=1, batch=256)
+    B = B_PER_GPU
+    while B > 64 and (args.steps + args.warmup) * B / probe > 120.0:
+        B //= 2
+    value, info = cpu_train_throughput(0, steps=args.steps, warmup=max(1, args.warmup), batch=B)
+    sample = (f"{args.steps} fp32 steps of {B} triplets (of the {B_PER_GPU}-triplet batch), oracle port of "
+              f"backend/training.py:36-53 with the embedding-only backbone, torch CPU, {info['cores']} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, "fp32", "f32") | {"cpu_sample_batch": B},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(world, precision, table_dtype):
+    return {
+        "workload": "configs[1] heavy GPU run shape: triplet training step, batch 2048/GPU, proj-dim 512, "
+                    "query 32 / doc 256 tokens (shape U), margin 0.3, Adam lr 1e-3, random-init 30522x384 tables",
+        "global_batch": B_PER_GPU * world, "batch_per_gpu": B_PER_GPU, "projection_dim": P_DIM, "Lq": LQ, "Ld": LD,
+        "parallelism": f"dp{world}", "projection_precision": precision, "table_dtype": table_dtype,
+        "l2": f"inputs rotate over {N_TOKEN_SETS} token batches (178 MB > 126 MB L2); the two token tables are "
+              "weights and stay cache-warm across steps as in real training",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA (sm_100a) device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from two_towers_overlords_b200 import TwoTowersModel, _native
+    from two_towers_overlords_b200.training import FusedTrainer
+
+    lib = _native.load()
+    table_dtype = torch.bfloat16 if args.table_dtype == "bf16" else torch.float32
+    torch.manual_seed(0)
+    model = TwoTowersModel(projection_dim=P_DIM, table_dtype=table_dtype, precision=args.precision).to(dev)
+    ids_dtype, mask_dtype = torch.int32, torch.uint8
+    trainer = FusedTrainer(model, MARGIN, LR, B_PER_GPU, LQ, LD, precision=args.precision, world_size=world, rank=rank,
+                           use_graph=not args.no_graph, ids_dtype=ids_dtype, mask_dtype=mask_dtype,
+                           token_slots=N_TOKEN_SETS)
+    host_sets = token_sets(N_TOKEN_SETS, B_PER_GPU, 1234 + rank, ids_dtype, mask_dtype, pin=True)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_sets[0])
+    for slot, hs in enumerate(host_sets):  # inputs resident in HBM for the `value` leg
+        for dst, src in zip(trainer.tok_slots[slot], hs):
+            dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, W = args.steps, args.warmup
+    for i in range(W):
+        trainer.step(i % N_TOKEN_SETS)
+    barrier()
+    launches_per_step = int(trainer.kernel_launches_per_step or 0)
+
+    # ---- leg 1: device-resident inputs -----------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.15 if sampler else 0.0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(K):
+        trainer.step((W + i) % N_TOKEN_SETS)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    loss_after = float(trainer.loss_view[0].item())
+    value = B_PER_GPU * world * K / (ms_total * 1e-3)
+
+    # ---- leg 2: end to end through the public API, host buffers --------------------------------------
+    # every step: pinned host tokens -> H2D (copy stream, two steps ahead at most) -> FusedTrainer.step -> loss D2H
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    loss_host = torch.zeros(K + W, dtype=torch.float32).pin_memory()
+    done = [None] * (K + W)
+    ready = [None] * (K + W)
+
+    def e2e_step(i):
+        slot = i % N_TOKEN_SETS
+        if i >= 2 and done[i - 2] is not None:
+            copy_stream.wait_event(done[i - 2])  # bounded prefetch; slot reuse is N_TOKEN_SETS steps away
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(trainer.tok_slots[slot], host_sets[slot]):
+                dst.copy_(src, non_blocking=True)
+            ready[i] = torch.cuda.Event()
+            ready[i].record(copy_stream)
+        main.wait_event(ready[i])
+        loss = trainer.step(slot)
+        loss_host[i: i + 1].copy_(loss.reshape(1), non_blocking=True)
+        done[i] = torch.cuda.Event()
+        done[i].record(main)
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(W, W + K):
+        e2e_step(i)
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e_value = B_PER_GPU * world * K / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: the pooled gather, timed alone on the launching stream -----
+    esz = 2 if table_dtype == torch.bfloat16 else 4
+    tok_per_triplet = LQ + 2 * LD
+    alg_bytes_per_triplet = tok_per_triplet * HIDDEN * esz + tok_per_triplet * (4 + 1) + 3 * (HIDDEN * 4 + 8)
+    segs = (_native.PoolSeg * 3)()
+    xhat = torch.empty(3 * B_PER_GPU, HIDDEN, dtype=torch.float32, device=dev)
+    cnt = torch.empty(3 * B_PER_GPU, dtype=torch.float32, device=dev)
+    nrm = torch.empty(3 * B_PER_GPU, dtype=torch.float32, device=dev)
+    tq = model.query_tower.pretrained_model.table.data
+    td = model.document_tower.pretrained_model.table.data
+
+    def pool_only(slot):
+        t = trainer.tok_slots[slot]
+        for s, (tab, ids, mask, L) in enumerate(((tq, t[0], t[1], LQ), (td, t[2], t[3], LD), (td, t[4], t[5], LD))):
+            segs[s].table, segs[s].ids, segs[s].mask = tab.data_ptr(), ids.data_ptr(), mask.data_ptr()
+            segs[s].B, segs[s].L, segs[s].row0 = B_PER_GPU, L, s * B_PER_GPU
+        _native.check(lib.tt_pool_fwd_multi(segs, 3, _native.dtype_code(tq), VOCAB, HIDDEN, _native.dtype_code(t[0]),
+                                            _native.dtype_code(t[1]), xhat.data_ptr(), cnt.data_ptr(), nrm.data_ptr(),
+                                            None, _native.stream()), "tt_pool_fwd_multi")
+
+    for i in range(max(3, W)):
+        pool_only(i % N_TOKEN_SETS)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        pool_only(i % N_TOKEN_SETS)
+    ev1.record()
+    torch.cuda.synchronize()
+    pool_ms = ev0.elapsed_time(ev1) / K
+    hbm_peak, tensor_peak, peak_kind = peaks()
+    achieved = alg_bytes_per_triplet * B_PER_GPU / (pool_ms * 1e-3) / 1e9
+    roofline = {
+        "kernel": "pool_fwd_kernel (token-row gather + masked mean + L2 normalise, q|p|n in one launch)",
+        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s",
+        "frac": achieved / hbm_peak, "traffic": None,
+        "algorithmic_bytes_per_launch": alg_bytes_per_triplet * B_PER_GPU, "us_per_launch": pool_ms * 1e3,
+        "share_of_step": pool_ms / (ms_total / K),
+        "note": "both 46.9 MB fp32 tables fit the 126 MB L2, so DRAM traffic is far below the algorithmic bytes "
+                "and frac can exceed 1 (SURVEY.md §7); see profiles/ for dram__bytes and L2 throughput",
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, info = cpu_train_throughput(args.cpu_budget)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
+               "sample": f"{info['steps']} fp32 steps of {info['batch']} triplets in {info['seconds']} s "
+                         f"(oracle/two_towers_oracle.train_step, torch CPU, {info['cores']} threads)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else f"f32 ({args.precision} tensor-core projection)",
+            "data": "synthetic", "config": workload_config(world, args.precision, args.table_dtype),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": launches_per_step * K, "gpu_launches_per_step": launches_per_step,
+            "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "loss_after": loss_after,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("TT_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--table-dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

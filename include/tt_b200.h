@@ -51,6 +51,8 @@ enum tt_precision {
 
 int tt_version(void);
 const char* tt_last_error(void);
+/* Diagnostics: kernels this library has launched (or captured into a CUDA graph) in this process so far. */
+unsigned long long tt_launch_count(void);
 /* sm count / compute capability of the current device; error if it is not sm_100. */
 int tt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -62,6 +62,7 @@ class StepArgs(ctypes.Structure):
 _SIGNATURES = {
     "tt_version": (c_int, []),
     "tt_last_error": (c_char_p, []),
+    "tt_launch_count": (ctypes.c_ulonglong, []),
     "tt_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tt_pool_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -24,6 +24,9 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
   return 1;
 }
 
+static unsigned long long g_launches = 0;
+void note_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int cached = 0;
   if (cached) return cached;
@@ -81,6 +84,7 @@ using namespace tt;
 
 extern "C" int tt_version(void) { return TT_B200_VERSION; }
 extern "C" const char* tt_last_error(void) { return tt::g_err; }
+extern "C" unsigned long long tt_launch_count(void) { return __atomic_load_n(&tt::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int tt_device_info(int* sms, int* cc_major, int* cc_minor) {
   int dev = 0;

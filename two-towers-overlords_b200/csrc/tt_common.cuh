@@ -27,7 +27,13 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line);
     }                                                                      \
   } while (0)
 
-#define TT_LAUNCH_CHECK() TT_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here; the count backs bench.py's "gpu_launches"
+void note_launch();
+#define TT_LAUNCH_CHECK()          \
+  do {                             \
+    ::tt::note_launch();           \
+    TT_CUDA(cudaGetLastError());   \
+  } while (0)
 
 static inline cudaStream_t as_stream(tt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

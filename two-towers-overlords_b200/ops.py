@@ -208,7 +208,8 @@ class TripletStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.args = N.StepArgs()
-        self._keep = None
+        self.slots = []
+        self._keep = []
 
     def bind(self, tokens, tables, params, grads, margin, inv_batch, grad_scale=1.0, table_grads=None):
         """tokens = (q_ids,q_mask,p_ids,p_mask,n_ids,n_mask) CUDA tensors; tables = (table_q, table_d);
@@ -238,10 +239,26 @@ class TripletStep:
         else:
             a.dtable_q, a.dtable_d = None, None
         a.precision, a.ws, a.ws_bytes = self.prec, N.ptr(self.ws), self.ws_bytes
-        self._keep = (tokens, tables, params, grads, table_grads)
+        self.slots = [a]
+        self._keep = [(tokens, tables, params, grads, table_grads)]
 
-    def run(self):
-        N.check(self.lib.tt_triplet_step(ctypes.byref(self.args), N.stream()), "tt_triplet_step")
+    def add_tokens(self, tokens) -> int:
+        """Another token-buffer set sharing every other argument (rotating / double-buffered inputs);
+        returns its slot index for run(slot)."""
+        B, Lq, Ld = self.shape[:3]
+        q_ids, q_mask, p_ids, p_mask, n_ids, n_mask = tokens
+        assert tuple(q_ids.shape) == (B, Lq) and tuple(p_ids.shape) == (B, Ld) and tuple(n_ids.shape) == (B, Ld)
+        a = N.StepArgs.from_buffer_copy(self.args)
+        assert N.dtype_code(q_ids) == a.ids_dtype and N.dtype_code(q_mask) == a.mask_dtype
+        a.q_ids, a.q_mask = N.ptr(q_ids), N.ptr(q_mask)
+        a.p_ids, a.p_mask = N.ptr(p_ids), N.ptr(p_mask)
+        a.n_ids, a.n_mask = N.ptr(n_ids), N.ptr(n_mask)
+        self.slots.append(a)
+        self._keep.append(tokens)
+        return len(self.slots) - 1
+
+    def run(self, slot: int = 0):
+        N.check(self.lib.tt_triplet_step(ctypes.byref(self.slots[slot]), N.stream()), "tt_triplet_step")
         return self.loss
 
 

@@ -122,7 +122,7 @@ class FusedTrainer:
     def __init__(self, model: TwoTowersModel, margin: float, lr: float, batch_size: int, Lq: int = 32, Ld: int = 256,
                  precision: Optional[str] = None, world_size: int = 1, rank: int = 0, use_graph: bool = True,
                  betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, ids_dtype=torch.int32,
-                 mask_dtype=torch.uint8):
+                 mask_dtype=torch.uint8, token_slots: int = 1):
         qt, dt = model.query_tower, model.document_tower
         self.model = model
         self.device = qt.pretrained_model.device
@@ -158,8 +158,12 @@ class FusedTrainer:
         self.loss_view = self.flat_g[self.n_param:]
         # static token buffers (graph replays read these addresses)
         mk = lambda L, dt_: torch.zeros(batch_size, L, dtype=dt_, device=dev)  # noqa: E731
-        self.tok = (mk(Lq, ids_dtype), mk(Lq, mask_dtype), mk(Ld, ids_dtype), mk(Ld, mask_dtype),
-                    mk(Ld, ids_dtype), mk(Ld, mask_dtype))
+        new_set = lambda: (mk(Lq, ids_dtype), mk(Lq, mask_dtype), mk(Ld, ids_dtype), mk(Ld, mask_dtype),  # noqa: E731
+                           mk(Ld, ids_dtype), mk(Ld, mask_dtype))
+        # token_slots > 1: rotating input buffers (prefetch step i+1 while step i computes; each slot has
+        # its own captured graph because a graph replays fixed addresses)
+        self.tok_slots = [new_set() for _ in range(max(1, token_slots))]
+        self.tok = self.tok_slots[0]
         self.table_grads = None
         if self.train_table:
             self.table_grads = (torch.zeros_like(qt.pretrained_model.table, dtype=torch.float32),
@@ -169,20 +173,23 @@ class FusedTrainer:
         self.step_obj.loss = self.loss_view  # loss lands in the flat gradient buffer's last slot
         self.step_obj.bind(self.tok, (qt.pretrained_model.table.data, dt.pretrained_model.table.data), self.p_views,
                            self.g_views, self.margin, 1.0 / (batch_size * world_size), 1.0, self.table_grads)
+        for toks in self.tok_slots[1:]:
+            self.step_obj.add_tokens(toks)
         self.use_graph = use_graph
-        self.graph_fb = self.graph_opt = None
+        self.graph_fb = [None] * len(self.tok_slots)
+        self.graph_opt = None
         self.steps_done = 0
         self.kernel_launches_per_step = None
 
     # -- pieces ------------------------------------------------------------------------------------
-    def load_tokens(self, q: TokenBatch, p: TokenBatch, n: TokenBatch):
+    def load_tokens(self, q: TokenBatch, p: TokenBatch, n: TokenBatch, slot: int = 0):
         """Host (pinned) or device token batches -> static device buffers, async on the current stream."""
-        for dst, src in zip(self.tok, (q.input_ids, q.attention_mask, p.input_ids, p.attention_mask,
-                                        n.input_ids, n.attention_mask)):
+        for dst, src in zip(self.tok_slots[slot], (q.input_ids, q.attention_mask, p.input_ids, p.attention_mask,
+                                                   n.input_ids, n.attention_mask)):
             dst.copy_(src, non_blocking=True)
 
-    def _fwd_bwd(self):
-        self.step_obj.run()
+    def _fwd_bwd(self, slot: int = 0):
+        self.step_obj.run(slot)
 
     def _optimizer(self):
         b1, b2 = self.betas
@@ -193,38 +200,48 @@ class FusedTrainer:
         # (table training uses a plain SGD-free path: the caller owns the table optimiser)
 
     def _capture(self):
-        # warm up on a side stream as torch requires, then capture
+        # warm up on a side stream as torch requires, then capture one graph per token slot
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self._fwd_bwd()
+            self._fwd_bwd(0)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_fb):
-            self._fwd_bwd()
-            if self.world == 1:
-                self._optimizer()
+        lib = ops.N.load()
+        for slot in range(len(self.tok_slots)):
+            n0 = lib.tt_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._fwd_bwd(slot)
+                if self.world == 1:
+                    self._optimizer()
+            self.graph_fb[slot] = g
+            self.kernel_launches_per_step = lib.tt_launch_count() - n0
         if self.world > 1:
+            n0 = lib.tt_launch_count()
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt):
                 self._optimizer()
+            self.kernel_launches_per_step += lib.tt_launch_count() - n0
 
-    def step(self) -> torch.Tensor:
-        """One optimiser step on the tokens currently in the static buffers; returns the (global) loss as
-        a device scalar — no host sync."""
+    def step(self, slot: int = 0) -> torch.Tensor:
+        """One optimiser step on the tokens currently in the static buffers of `slot`; returns the (global)
+        loss as a device scalar — no host sync."""
         if self.use_graph:
-            if self.graph_fb is None:
+            if self.graph_fb[0] is None:
                 self._capture()  # warm-up runs forward/backward only, capture itself executes nothing
-            self.graph_fb.replay()
+            self.graph_fb[slot].replay()
             if self.world > 1:
                 torch.distributed.all_reduce(self.flat_g, group=self.pg)
                 self.graph_opt.replay()
         else:
-            self._fwd_bwd()
+            lib = ops.N.load()
+            n0 = lib.tt_launch_count()
+            self._fwd_bwd(slot)
             if self.world > 1:
                 torch.distributed.all_reduce(self.flat_g, group=self.pg)
             self._optimizer()
+            self.kernel_launches_per_step = lib.tt_launch_count() - n0
         self.steps_done += 1
         return self.loss_view[0]
 
