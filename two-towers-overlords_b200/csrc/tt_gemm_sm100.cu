@@ -1,0 +1,686 @@
+// Tensor-core projection path (TT_PREC_BF16X3 / TT_PREC_BF16): every contraction of the tower MLP, forward and
+// backward, runs on tcgen05.mma with TMA-fed, 128-byte-swizzled shared-memory operands and fp32 accumulators in
+// TMEM.  Replaces backend/model.py:33-38,59 and what autograd does for it inside backend/training.py:50.
+//
+// One kernel, gemm_tn_kernel:   C[m,n] = epi( sum_pairs sum_k A_pair[m,k] * B_pair[n,k] )
+//   * both operands K-major bf16 (row-major with K contiguous); transposed copies are produced by the upstream
+//     epilogues / a tiled transpose kernel so that no contraction needs an MN-major descriptor;
+//   * bf16x3: fp32 values are carried as (hi, lo) bf16 pairs and the product is hi*hi + hi*lo + lo*hi, three MMAs
+//     into the same TMEM accumulator (~2^-17 relative error: inside the 1e-4 loss / 1e-3 gradient gates);
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
+//     (tcgen05.ld 32 lanes x 16 columns per warp quarter), STAGES-deep mbarrier ring between producer and issuer;
+//   * up to two problem groups per launch (query tower | document tower) and split-K over blockIdx.z for the
+//     weight-gradient contractions (K = batch rows), reduced afterwards in a fixed order (deterministic).
+#include "tt_ptx.cuh"
+#include "tt_simt.cuh"
+#include "tt_sm100.cuh"
+#include "tt_tma.cuh"
+
+namespace tt {
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+using namespace ptx;
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kStages = 6;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct alignas(64) GemmGroup {
+  CUtensorMap a[3], b[3];  // bf16 terms of each operand: hi, lo (= fp32 - hi), lo2 (= fp32 - hi - lo)
+  int M, N, K, relu;
+  const float* bias;   // [N] nullable
+  const float* gate;   // [M, ldc] nullable: result is zeroed where gate <= 0 (ReLU backward)
+  float* C;            // [M, ldc] nullable
+  float* partial;      // [splits, M, N] when splits > 1 (raw sums, no epilogue)
+  bf16 *C_hi, *C_lo;   // [M, ldc] nullable: bf16 split of the result
+  bf16 *Ct_hi, *Ct_lo; // [N, ldt] nullable: transposed split, column = m
+  int ldc, ldt;
+  int pad[2];
+};
+
+struct alignas(64) GemmParams {
+  GemmGroup g[2];
+  int ngroups, splits, n_pairs, pad;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gi = blockIdx.z / p.splits, split = blockIdx.z - gi * p.splits;
+  const GemmGroup& g = p.g[gi];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= g.M || n0 >= g.N) return;  // CTA-uniform: the grid is sized for the larger group
+
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int kb_per = (kb_total + p.splits - 1) / p.splits;
+  const int kb0 = split * kb_per;
+  const int kb1 = min(kb0 + kb_per, kb_total);
+  const int n_iter = (kb1 - kb0) * p.n_pairs;  // >= 1: the host never creates an empty split
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&g.a[0]);
+    prefetch_tensormap(&g.b[0]);
+    if (p.n_pairs > 1) {
+      prefetch_tensormap(&g.a[1]);
+      prefetch_tensormap(&g.b[1]);
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer --------------------------------------------------------------------
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int pair = it % p.n_pairs, kb = kb0 + it / p.n_pairs;
+        // product terms in order: hi*hi, hi*lo, lo*hi | lo*lo, hi*lo2, lo2*hi  (1, 3 or 6 of them)
+        const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
+        const CUtensorMap* ma = &g.a[ai];
+        const CUtensorMap* mb = &g.b[bi];
+        mbar_arrive_expect_tx(&full[s], kStageBytes);
+        tma_load_2d(smem + s * kStageBytes, ma, &full[s], kb * BK, m0);
+        tma_load_2d(smem + s * kStageBytes + kABytes, mb, &full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer ------------------------------------------------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+        const uint64_t da = make_smem_desc_sw128(a_addr), db = make_smem_desc_sw128(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
+          mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+        mma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+      }
+      mma_commit(tmem_full);
+    }
+  } else {  // ---- epilogue: warp quarter q owns TMEM lanes [32q, 32q+32) -----------------------------------
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < g.M;
+    const bool raw_out = g.partial != nullptr;
+    for (int c = 0; c < BN / 16; ++c) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
+      const int n = n0 + c * 16;
+      if (n >= g.N) break;  // warp-uniform
+      if (raw_out) {
+        if (row_ok) {
+          float4* dst = reinterpret_cast<float4*>(g.partial + ((size_t)split * g.M + m) * g.N + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        continue;
+      }
+      if (g.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __ldg(g.bias + n + j);
+      }
+      if (g.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      const size_t o = (size_t)m * g.ldc + n;
+      if (g.gate && row_ok) {
+        const float4* gp = reinterpret_cast<const float4*>(g.gate + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = __ldg(gp + j);
+          v[4 * j + 0] = t.x > 0.f ? v[4 * j + 0] : 0.f;
+          v[4 * j + 1] = t.y > 0.f ? v[4 * j + 1] : 0.f;
+          v[4 * j + 2] = t.z > 0.f ? v[4 * j + 2] : 0.f;
+          v[4 * j + 3] = t.w > 0.f ? v[4 * j + 3] : 0.f;
+        }
+      }
+      if (!row_ok) continue;
+      if (g.C) {
+        float4* dst = reinterpret_cast<float4*>(g.C + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (g.C_hi || g.Ct_hi) {
+        alignas(16) bf16 hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_bf16(v[j], hi[j], lo[j]);
+        if (g.C_hi) {
+          uint4* dh = reinterpret_cast<uint4*>(g.C_hi + o);
+          uint4* dl = reinterpret_cast<uint4*>(g.C_lo + o);
+          dh[0] = reinterpret_cast<const uint4*>(hi)[0];
+          dh[1] = reinterpret_cast<const uint4*>(hi)[1];
+          dl[0] = reinterpret_cast<const uint4*>(lo)[0];
+          dl[1] = reinterpret_cast<const uint4*>(lo)[1];
+        }
+        if (g.Ct_hi) {  // lanes hold consecutive m: each store is one coalesced 64 B run per column
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            g.Ct_hi[(size_t)(n + j) * g.ldt + m] = hi[j];
+            g.Ct_lo[(size_t)(n + j) * g.ldt + m] = lo[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// out[i] = (accumulate ? out[i] : 0) + sum_z partial[z][i], z ascending: fixed order, no atomics
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n,
+                                                            float* __restrict__ out, int accumulate) {
+  const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = accumulate ? *reinterpret_cast<const float4*>(out + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < splits; ++z) {
+    const float4 t = *reinterpret_cast<const float4*>(partial + (size_t)z * n + i);
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+
+// fp32 [R, C] (pitch ld) -> bf16 hi/lo [R, C] and, optionally, transposed hi/lo [C, ldt] (column = row index + tcol0)
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ X, int R, int C, long long ld,
+                                                              bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                              bf16* __restrict__ lo2, bf16* __restrict__ thi,
+                                                              bf16* __restrict__ tlo, int ldt, int tcol0) {
+  __shared__ bf16 s_hi[32][33], s_lo[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    bf16 h = __float2bfloat16_rn(0.f), l = h;
+    if (r < R && c < C) {
+      const float xv = X[(size_t)r * ld + c];
+      split_bf16(xv, h, l);
+      if (hi) {
+        hi[(size_t)r * C + c] = h;
+        lo[(size_t)r * C + c] = l;
+      }
+      if (lo2) lo2[(size_t)r * C + c] = __float2bfloat16_rn((xv - __bfloat162float(h)) - __bfloat162float(l));
+    }
+    s_hi[ty + i * 8][tx] = h;
+    s_lo[ty + i * 8][tx] = l;
+  }
+  if (!thi) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < R && c < C) {
+      thi[(size_t)c * ldt + tcol0 + r] = s_hi[tx][ty + i * 8];
+      tlo[(size_t)c * ldt + tcol0 + r] = s_lo[tx][ty + i * 8];
+    }
+  }
+}
+
+// bf16 hi/lo [R, C] -> transposed hi/lo [C, ldt], column = tcol0 + r
+__global__ void __launch_bounds__(256) transpose_pair_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo,
+                                                             int R, int C, bf16* __restrict__ thi,
+                                                             bf16* __restrict__ tlo, int ldt, int tcol0) {
+  __shared__ bf16 s[2][32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    if (r < R && c < C) {
+      s[0][ty + i * 8][tx] = hi[(size_t)r * C + c];
+      s[1][ty + i * 8][tx] = lo[(size_t)r * C + c];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < R && c < C) {
+      thi[(size_t)c * ldt + tcol0 + r] = s[0][tx][ty + i * 8];
+      tlo[(size_t)c * ldt + tcol0 + r] = s[1][tx][ty + i * 8];
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+struct Operand {  // a K-major bf16 (hi, lo[, lo2]) split: [rows, K] with pitch ld
+  const bf16* hi;
+  const bf16* lo;
+  long long ld;
+  const bf16* lo2 = nullptr;
+};
+
+struct GemmDesc {
+  Operand A, B;
+  int M, N, K;
+  const float* bias = nullptr;
+  int relu = 0;
+  const float* gate = nullptr;
+  float* C = nullptr;
+  int ldc = 0;
+  bf16 *C_hi = nullptr, *C_lo = nullptr, *Ct_hi = nullptr, *Ct_lo = nullptr;
+  int ldt = 0;
+};
+
+int fill_group(GemmGroup& g, const GemmDesc& d, int n_pairs) {
+  int rc;
+  const bf16* at[3] = {d.A.hi, d.A.lo, d.A.lo2};
+  const bf16* bt[3] = {d.B.hi, d.B.lo, d.B.lo2};
+  const int terms = n_pairs == 1 ? 1 : (n_pairs == 3 ? 2 : 3);
+  for (int i = 0; i < 3; ++i) {
+    if (i < terms) {
+      TT_REQUIRE(at[i] && bt[i], "gemm: operand term %d missing for a %d-product contraction", i, n_pairs);
+      if ((rc = make_map_bf16_kmajor(&g.a[i], at[i], d.M, d.K, d.A.ld, BM))) return rc;
+      if ((rc = make_map_bf16_kmajor(&g.b[i], bt[i], d.N, d.K, d.B.ld, BN))) return rc;
+    } else {
+      g.a[i] = g.a[0];
+      g.b[i] = g.b[0];
+    }
+  }
+  g.M = d.M; g.N = d.N; g.K = d.K; g.relu = d.relu;
+  g.bias = d.bias; g.gate = d.gate; g.C = d.C; g.partial = nullptr;
+  g.C_hi = d.C_hi; g.C_lo = d.C_lo; g.Ct_hi = d.Ct_hi; g.Ct_lo = d.Ct_lo;
+  g.ldc = d.ldc ? d.ldc : d.N;
+  g.ldt = d.ldt;
+  return 0;
+}
+
+int ensure_gemm_attr() {
+  static bool done = false;
+  if (done) return 0;
+  TT_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+  done = true;
+  return 0;
+}
+
+// Launches 1 or 2 problem groups.  partial != nullptr: every group is a split-K contraction whose raw partial sums
+// go to `partial` ([group][split][M*N], groups packed back to back) and are then reduced into d.C (+= if accumulate).
+int launch_gemm(const GemmDesc* d, int ngroups, int n_pairs, int splits, float* partial, int accumulate,
+                cudaStream_t st) {
+  int rc;
+  if ((rc = ensure_gemm_attr())) return rc;
+  GemmParams p{};
+  p.ngroups = ngroups;
+  p.n_pairs = n_pairs;
+  int tiles_m = 0, tiles_n = 0;
+  for (int i = 0; i < ngroups; ++i) {
+    TT_REQUIRE(d[i].M >= 1 && d[i].N >= 16 && d[i].N % 16 == 0 && d[i].K >= 1, "gemm: bad shape M=%d N=%d K=%d", d[i].M,
+               d[i].N, d[i].K);
+    if ((rc = fill_group(p.g[i], d[i], n_pairs))) return rc;
+    tiles_m = max(tiles_m, (d[i].M + BM - 1) / BM);
+    tiles_n = max(tiles_n, (d[i].N + BN - 1) / BN);
+  }
+  const bool use_partial = partial != nullptr;
+  if (!use_partial) splits = 1;
+  if (splits > 1) {
+    // all groups of a split-K launch share K (same batch rows) up to the tower split; clamp to the smallest
+    int kb_min = 1 << 30;
+    for (int i = 0; i < ngroups; ++i) kb_min = min(kb_min, (d[i].K + BK - 1) / BK);
+    splits = min(splits, kb_min);
+    // no empty split for any group: ceil(kb/ceil(kb/splits)) must equal splits for every group
+    for (bool ok = false; !ok && splits > 1;) {
+      ok = true;
+      for (int i = 0; i < ngroups; ++i) {
+        const int kb = (d[i].K + BK - 1) / BK, per = (kb + splits - 1) / splits;
+        if ((kb + per - 1) / per != splits) ok = false;
+      }
+      if (!ok) --splits;
+    }
+  }
+  p.splits = splits;
+  if (use_partial) {
+    size_t off = 0;
+    for (int i = 0; i < ngroups; ++i) {
+      p.g[i].partial = partial + off;
+      off += (size_t)splits * d[i].M * d[i].N;
+    }
+  }
+  dim3 grid(tiles_n, tiles_m, ngroups * splits);
+  gemm_tn_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(p);
+  TT_LAUNCH_CHECK();
+  if (use_partial) {
+    for (int i = 0; i < ngroups; ++i) {
+      const size_t n = (size_t)d[i].M * d[i].N;
+      TT_REQUIRE(d[i].ldc == 0 || d[i].ldc == d[i].N, "gemm: split-K output must be dense");
+      splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(p.g[i].partial, splits, n, d[i].C,
+                                                                           accumulate);
+      TT_LAUNCH_CHECK();
+    }
+  } else {
+    TT_REQUIRE(!accumulate, "gemm: accumulate needs the split-K path");  // checked before the launch in practice
+  }
+  return 0;
+}
+
+int choose_splits(int tiles, int K) {
+  const int kb = (K + BK - 1) / BK;
+  int s = (2 * sm_count() + tiles - 1) / tiles;
+  s = min(s, kb);
+  s = min(s, 32);
+  return max(s, 2);  // weight-gradient GEMMs always take the split-K path (it also implements `accumulate`)
+}
+
+int split_transpose(const float* X, int R, int C, long long ld, bf16* hi, bf16* lo, bf16* thi, bf16* tlo, int ldt,
+                    int tcol0, cudaStream_t st, bf16* lo2 = nullptr) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  split_transpose_kernel<<<grid, 256, 0, st>>>(X, R, C, ld, hi, lo, lo2, thi, tlo, ldt, tcol0);
+  TT_LAUNCH_CHECK();
+  return 0;
+}
+
+int transpose_pair(const bf16* hi, const bf16* lo, int R, int C, bf16* thi, bf16* tlo, int ldt, int tcol0,
+                   cudaStream_t st) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  transpose_pair_kernel<<<grid, 256, 0, st>>>(hi, lo, R, C, thi, tlo, ldt, tcol0);
+  TT_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int round64(int x) { return (x + 63) / 64 * 64; }
+
+// ---- workspace of one tower pass (standalone tt_encode_fwd / tt_encode_bwd) --------------------------------
+struct MlpWs {
+  bf16 *x_hi, *x_lo, *x_lo2, *xt_hi, *xt_lo;  // [M,H], [H,ldm]
+  bf16 *w1_hi, *w1_lo, *w1_lo2, *w1t_hi, *w1t_lo;  // [P,H], [H,P]
+  bf16 *w2_hi, *w2_lo, *w2t_hi, *w2t_lo;      // [P,P], [P,P]
+  bf16 *h_hi, *h_lo, *ht_hi, *ht_lo;          // [M,P], [P,ldm]
+  bf16 *dy_hi, *dy_lo, *dyt_hi, *dyt_lo;      // [M,P], [P,ldm]
+  bf16 *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;      // [M,P], [P,ldm]
+  float *hbuf, *dz1, *partial, *colsum;
+  int ldm;
+};
+
+size_t carve_mlp_ws(char* base, int M, int H, int P, MlpWs* out) {
+  char* p = base;
+  MlpWs w{};
+  const int ldm = round64(M);
+  w.ldm = ldm;
+  const size_t MH = (size_t)M * H, MP = (size_t)M * P, HL = (size_t)H * ldm, PL = (size_t)P * ldm;
+  w.x_hi = ws_take<bf16>(p, MH); w.x_lo = ws_take<bf16>(p, MH); w.x_lo2 = ws_take<bf16>(p, MH);
+  w.xt_hi = ws_take<bf16>(p, HL); w.xt_lo = ws_take<bf16>(p, HL);
+  w.w1_hi = ws_take<bf16>(p, (size_t)P * H); w.w1_lo = ws_take<bf16>(p, (size_t)P * H);
+  w.w1_lo2 = ws_take<bf16>(p, (size_t)P * H);
+  w.w1t_hi = ws_take<bf16>(p, (size_t)P * H); w.w1t_lo = ws_take<bf16>(p, (size_t)P * H);
+  w.w2_hi = ws_take<bf16>(p, (size_t)P * P); w.w2_lo = ws_take<bf16>(p, (size_t)P * P);
+  w.w2t_hi = ws_take<bf16>(p, (size_t)P * P); w.w2t_lo = ws_take<bf16>(p, (size_t)P * P);
+  w.h_hi = ws_take<bf16>(p, MP); w.h_lo = ws_take<bf16>(p, MP);
+  w.ht_hi = ws_take<bf16>(p, PL); w.ht_lo = ws_take<bf16>(p, PL);
+  w.dy_hi = ws_take<bf16>(p, MP); w.dy_lo = ws_take<bf16>(p, MP);
+  w.dyt_hi = ws_take<bf16>(p, PL); w.dyt_lo = ws_take<bf16>(p, PL);
+  w.dz_hi = ws_take<bf16>(p, MP); w.dz_lo = ws_take<bf16>(p, MP);
+  w.dzt_hi = ws_take<bf16>(p, PL); w.dzt_lo = ws_take<bf16>(p, PL);
+  w.hbuf = ws_take<float>(p, MP);
+  w.dz1 = ws_take<float>(p, MP);
+  w.partial = ws_take<float>(p, (size_t)32 * P * max(P, H));
+  w.colsum = ws_take<float>(p, (size_t)2 * kColsumSlices * P);
+  if (out) *out = w;
+  return (size_t)(p - base) + 256;
+}
+
+}  // namespace
+
+size_t mlp_sm100_ws_bytes(int M, int H, int P) { return carve_mlp_ws(nullptr, M, H, P, nullptr); }
+
+int mlp_fwd_sm100(const float* x, int M, int H, int P, const float* W1, const float* b1, const float* W2,
+                  const float* b2, float* h, float* y, int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TT_REQUIRE(ws_bytes >= mlp_sm100_ws_bytes(M, H, P), "tt_encode_fwd: workspace too small");
+  MlpWs w;
+  carve_mlp_ws(reinterpret_cast<char*>(ws), M, H, P, &w);
+  const int np = precision == TT_PREC_BF16X3 ? 3 : 1;
+  // the first layer feeds the ReLU whose sign gates the backward: it gets the 6-product (fp32-exact) split
+  const int np1 = precision == TT_PREC_BF16X3 ? 6 : 1;
+  int rc;
+  if ((rc = split_transpose(x, M, H, H, w.x_hi, w.x_lo, nullptr, nullptr, 0, 0, st, w.x_lo2))) return rc;
+  if ((rc = split_transpose(W1, P, H, H, w.w1_hi, w.w1_lo, nullptr, nullptr, 0, 0, st, w.w1_lo2))) return rc;
+  if ((rc = split_transpose(W2, P, P, P, w.w2_hi, w.w2_lo, nullptr, nullptr, 0, 0, st))) return rc;
+  GemmDesc g1{};
+  g1.A = {w.x_hi, w.x_lo, H, w.x_lo2}; g1.B = {w.w1_hi, w.w1_lo, H, w.w1_lo2};
+  g1.M = M; g1.N = P; g1.K = H; g1.bias = b1; g1.relu = 1;
+  g1.C = h ? h : w.hbuf; g1.ldc = P; g1.C_hi = w.h_hi; g1.C_lo = w.h_lo;
+  if ((rc = launch_gemm(&g1, 1, np1, 1, nullptr, 0, st))) return rc;
+  GemmDesc g2{};
+  g2.A = {w.h_hi, w.h_lo, P}; g2.B = {w.w2_hi, w.w2_lo, P};
+  g2.M = M; g2.N = P; g2.K = P; g2.bias = b2; g2.C = y; g2.ldc = P;
+  return launch_gemm(&g2, 1, np, 1, nullptr, 0, st);
+}
+
+int mlp_bwd_sm100(const float* dy, const float* x, const float* h, const float* W1, const float* W2, int M, int H,
+                  int P, float* dW1, float* db1, float* dW2, float* db2, float* dx, int accumulate, int precision,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+  TT_REQUIRE(ws_bytes >= mlp_sm100_ws_bytes(M, H, P), "tt_encode_bwd: workspace too small");
+  MlpWs w;
+  carve_mlp_ws(reinterpret_cast<char*>(ws), M, H, P, &w);
+  const int np = precision == TT_PREC_BF16X3 ? 3 : 1;
+  const int ldm = w.ldm;
+  int rc;
+  // operands: dy, h, x (row-major + transposed), W2^T, W1^T
+  if ((rc = split_transpose(dy, M, P, P, w.dy_hi, w.dy_lo, w.dyt_hi, w.dyt_lo, ldm, 0, st))) return rc;
+  if ((rc = split_transpose(h, M, P, P, nullptr, nullptr, w.ht_hi, w.ht_lo, ldm, 0, st))) return rc;
+  if ((rc = split_transpose(x, M, H, H, nullptr, nullptr, w.xt_hi, w.xt_lo, ldm, 0, st))) return rc;
+  if ((rc = split_transpose(W2, P, P, P, nullptr, nullptr, w.w2t_hi, w.w2t_lo, P, 0, st))) return rc;
+  // db2, dW2 = dy^T h
+  if ((rc = colsum2(dy, M, db2, nullptr, 0, nullptr, P, P, accumulate, w.colsum, st))) return rc;
+  GemmDesc gw2{};
+  gw2.A = {w.dyt_hi, w.dyt_lo, ldm}; gw2.B = {w.ht_hi, w.ht_lo, ldm};
+  gw2.M = P; gw2.N = P; gw2.K = M; gw2.C = dW2;
+  const int tiles2 = ((P + BM - 1) / BM) * ((P + BN - 1) / BN);
+  if ((rc = launch_gemm(&gw2, 1, np, choose_splits(tiles2, M), w.partial, accumulate, st))) return rc;
+  // dz1 = (dy W2) * (h > 0)
+  GemmDesc gz{};
+  gz.A = {w.dy_hi, w.dy_lo, P}; gz.B = {w.w2t_hi, w.w2t_lo, P};
+  gz.M = M; gz.N = P; gz.K = P; gz.gate = h; gz.C = w.dz1; gz.ldc = P;
+  gz.C_hi = dx ? w.dz_hi : nullptr; gz.C_lo = dx ? w.dz_lo : nullptr;
+  gz.Ct_hi = w.dzt_hi; gz.Ct_lo = w.dzt_lo; gz.ldt = ldm;
+  if ((rc = launch_gemm(&gz, 1, np, 1, nullptr, 0, st))) return rc;
+  if ((rc = colsum2(w.dz1, M, db1, nullptr, 0, nullptr, P, P, accumulate, w.colsum, st))) return rc;
+  // dW1 = dz1^T x
+  GemmDesc gw1{};
+  gw1.A = {w.dzt_hi, w.dzt_lo, ldm}; gw1.B = {w.xt_hi, w.xt_lo, ldm};
+  gw1.M = P; gw1.N = H; gw1.K = M; gw1.C = dW1;
+  const int tiles1 = ((P + BM - 1) / BM) * ((H + BN - 1) / BN);
+  if ((rc = launch_gemm(&gw1, 1, np, choose_splits(tiles1, M), w.partial, accumulate, st))) return rc;
+  if (dx) {  // dx = dz1 W1
+    if ((rc = split_transpose(W1, P, H, H, nullptr, nullptr, w.w1t_hi, w.w1t_lo, P, 0, st))) return rc;
+    GemmDesc gx{};
+    gx.A = {w.dz_hi, w.dz_lo, P}; gx.B = {w.w1t_hi, w.w1t_lo, P};
+    gx.M = M; gx.N = H; gx.K = P; gx.C = dx; gx.ldc = H;
+    if ((rc = launch_gemm(&gx, 1, np, 1, nullptr, 0, st))) return rc;
+  }
+  return 0;
+}
+
+// ================================================================================================================
+// whole triplet step on the tensor cores: rows [0,B) = queries (query tower), rows [B,3B) = positives | negatives
+// (document tower).  Every GEMM launch carries both towers as two problem groups.
+// ================================================================================================================
+namespace {
+
+struct StepWs {
+  int ldt, dcol;  // transposed buffers: query rows at columns [0,B), document rows at [dcol, dcol+2B)
+  bf16 *x_hi, *x_lo, *x_lo2, *xt_hi, *xt_lo;  // [3B,H], [H,ldt]
+  bf16 *h_hi, *h_lo, *ht_hi, *ht_lo;        // [3B,P], [P,ldt]
+  bf16 *dy_hi, *dy_lo, *dyt_hi, *dyt_lo;    // [3B,P], [P,ldt]
+  bf16 *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;    // [3B,P], [P,ldt]
+  bf16 *w1_hi[2], *w1_lo[2], *w1_lo2[2], *w1t_hi[2], *w1t_lo[2];  // per tower: [P,H], [H,P]
+  bf16 *w2_hi[2], *w2_lo[2], *w2t_hi[2], *w2t_lo[2];  // per tower: [P,P], [P,P]
+  float *dz1, *partial, *colsum;
+};
+
+size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out) {
+  char* p = base;
+  StepWs w{};
+  w.dcol = round64(B);
+  w.ldt = w.dcol + round64(2 * B);
+  const size_t R = (size_t)3 * B;
+  w.x_hi = ws_take<bf16>(p, R * H); w.x_lo = ws_take<bf16>(p, R * H); w.x_lo2 = ws_take<bf16>(p, R * H);
+  w.xt_hi = ws_take<bf16>(p, (size_t)H * w.ldt); w.xt_lo = ws_take<bf16>(p, (size_t)H * w.ldt);
+  w.h_hi = ws_take<bf16>(p, R * P); w.h_lo = ws_take<bf16>(p, R * P);
+  w.ht_hi = ws_take<bf16>(p, (size_t)P * w.ldt); w.ht_lo = ws_take<bf16>(p, (size_t)P * w.ldt);
+  w.dy_hi = ws_take<bf16>(p, R * P); w.dy_lo = ws_take<bf16>(p, R * P);
+  w.dyt_hi = ws_take<bf16>(p, (size_t)P * w.ldt); w.dyt_lo = ws_take<bf16>(p, (size_t)P * w.ldt);
+  w.dz_hi = ws_take<bf16>(p, R * P); w.dz_lo = ws_take<bf16>(p, R * P);
+  w.dzt_hi = ws_take<bf16>(p, (size_t)P * w.ldt); w.dzt_lo = ws_take<bf16>(p, (size_t)P * w.ldt);
+  for (int t = 0; t < 2; ++t) {
+    w.w1_hi[t] = ws_take<bf16>(p, (size_t)P * H); w.w1_lo[t] = ws_take<bf16>(p, (size_t)P * H);
+    w.w1_lo2[t] = ws_take<bf16>(p, (size_t)P * H);
+    w.w1t_hi[t] = ws_take<bf16>(p, (size_t)P * H); w.w1t_lo[t] = ws_take<bf16>(p, (size_t)P * H);
+    w.w2_hi[t] = ws_take<bf16>(p, (size_t)P * P); w.w2_lo[t] = ws_take<bf16>(p, (size_t)P * P);
+    w.w2t_hi[t] = ws_take<bf16>(p, (size_t)P * P); w.w2t_lo[t] = ws_take<bf16>(p, (size_t)P * P);
+  }
+  w.dz1 = ws_take<float>(p, R * P);
+  w.partial = ws_take<float>(p, (size_t)2 * 32 * P * max(P, H));
+  w.colsum = ws_take<float>(p, (size_t)2 * kColsumSlices * P);
+  (void)train_table;
+  if (out) *out = w;
+  return (size_t)(p - base) + 256;
+}
+
+}  // namespace
+
+size_t step_sm100_ws_bytes(int B, int H, int P, int train_table) { return carve_step(nullptr, B, H, P, train_table, nullptr); }
+
+int step_sm100(const StepSm100& s, cudaStream_t st) {
+  const int B = s.B, H = s.H, P = s.P, np = s.n_split;
+  TT_REQUIRE(s.ws && s.ws_bytes >= step_sm100_ws_bytes(B, H, P, s.dxhat != nullptr), "tt_triplet_step: tensor-core workspace too small");
+  StepWs w;
+  carve_step(reinterpret_cast<char*>(s.ws), B, H, P, s.dxhat != nullptr, &w);
+  int rc;
+  const float* W1[2] = {s.Wq1, s.Wd1};
+  const float* W2[2] = {s.Wq2, s.Wd2};
+  const float* b1[2] = {s.bq1, s.bd1};
+  const float* b2[2] = {s.bq2, s.bd2};
+  float* dW1[2] = {s.dWq1, s.dWd1};
+  float* db1[2] = {s.dbq1, s.dbd1};
+  float* dW2[2] = {s.dWq2, s.dWd2};
+  float* db2[2] = {s.dbq2, s.dbd2};
+  const int row0[2] = {0, B}, rows[2] = {B, 2 * B}, tcol[2] = {0, w.dcol};
+
+  // 1. pooled gather: fp32 xhat + its bf16 split (row-major); the transposed copy comes from a tiled transpose
+  PoolParams pp = s.pool;
+  pp.x_hi = w.x_hi; pp.x_lo = w.x_lo; pp.x_lo2 = (np == 3) ? w.x_lo2 : nullptr; pp.xt_hi = nullptr; pp.xt_lo = nullptr;
+  if ((rc = pool_fwd_launch(pp, s.table_dtype, H, st))) return rc;
+  for (int t = 0; t < 2; ++t)
+    if ((rc = transpose_pair(w.x_hi + (size_t)row0[t] * H, w.x_lo + (size_t)row0[t] * H, rows[t], H, w.xt_hi, w.xt_lo,
+                             w.ldt, tcol[t], st)))
+      return rc;
+  // 2. weights of both towers -> bf16 splits (+ transposes for the backward contractions)
+  for (int t = 0; t < 2; ++t) {
+    if ((rc = split_transpose(W1[t], P, H, H, w.w1_hi[t], w.w1_lo[t], s.dxhat ? w.w1t_hi[t] : nullptr,
+                              s.dxhat ? w.w1t_lo[t] : nullptr, P, 0, st, w.w1_lo2[t])))
+      return rc;
+    if ((rc = split_transpose(W2[t], P, P, P, w.w2_hi[t], w.w2_lo[t], w.w2t_hi[t], w.w2t_lo[t], P, 0, st))) return rc;
+  }
+  // 3. h = relu(x W1^T + b1)  (fp32 + split + transposed split)
+  GemmDesc g[2];
+  for (int t = 0; t < 2; ++t) {
+    g[t] = GemmDesc{};
+    g[t].A = {w.x_hi + (size_t)row0[t] * H, w.x_lo + (size_t)row0[t] * H, H, w.x_lo2 + (size_t)row0[t] * H};
+    g[t].B = {w.w1_hi[t], w.w1_lo[t], H, w.w1_lo2[t]};
+    g[t].M = rows[t]; g[t].N = P; g[t].K = H; g[t].bias = b1[t]; g[t].relu = 1;
+    g[t].C = s.h + (size_t)row0[t] * P; g[t].ldc = P;
+    g[t].C_hi = w.h_hi + (size_t)row0[t] * P; g[t].C_lo = w.h_lo + (size_t)row0[t] * P;
+    g[t].Ct_hi = w.ht_hi + tcol[t]; g[t].Ct_lo = w.ht_lo + tcol[t]; g[t].ldt = w.ldt;
+  }
+  // (6-product split for this layer only: its ReLU sign gates the backward, see mlp_fwd_sm100)
+  if ((rc = launch_gemm(g, 2, np == 3 ? 6 : 1, 1, nullptr, 0, st))) return rc;
+  // 4. y = h W2^T + b2
+  for (int t = 0; t < 2; ++t) {
+    g[t] = GemmDesc{};
+    g[t].A = {w.h_hi + (size_t)row0[t] * P, w.h_lo + (size_t)row0[t] * P, P};
+    g[t].B = {w.w2_hi[t], w.w2_lo[t], P};
+    g[t].M = rows[t]; g[t].N = P; g[t].K = P; g[t].bias = b2[t];
+    g[t].C = s.y + (size_t)row0[t] * P; g[t].ldc = P;
+  }
+  if ((rc = launch_gemm(g, 2, np, 1, nullptr, 0, st))) return rc;
+  // 5. loss and its gradient (fp32 CUDA-core kernels; dY leaves as fp32 + bf16 split)
+  const float* yq = s.y;
+  const float* yp = s.y + (size_t)B * P;
+  const float* yn = s.y + (size_t)2 * B * P;
+  if ((rc = triplet_loss_fwd(yq, yp, yn, B, P, s.margin, s.inv_batch, s.stats, s.loss, st))) return rc;
+  LossSplitOut so{};
+  so.dy_hi = w.dy_hi; so.dy_lo = w.dy_lo;
+  if ((rc = triplet_loss_bwd(yq, yp, yn, s.stats, nullptr, s.grad_scale, B, P, s.inv_batch, s.dy, s.dy + (size_t)B * P,
+                             s.dy + (size_t)2 * B * P, &so, st)))
+    return rc;
+  for (int t = 0; t < 2; ++t)
+    if ((rc = transpose_pair(w.dy_hi + (size_t)row0[t] * P, w.dy_lo + (size_t)row0[t] * P, rows[t], P, w.dyt_hi,
+                             w.dyt_lo, w.ldt, tcol[t], st)))
+      return rc;
+  // 6. db2, dW2 = dY^T h   (split-K over the batch rows)
+  if ((rc = colsum2(s.dy, rows[0], db2[0], s.dy + (size_t)row0[1] * P, rows[1], db2[1], P, P, 0, w.colsum, st))) return rc;
+  for (int t = 0; t < 2; ++t) {
+    g[t] = GemmDesc{};
+    g[t].A = {w.dyt_hi + tcol[t], w.dyt_lo + tcol[t], w.ldt};
+    g[t].B = {w.ht_hi + tcol[t], w.ht_lo + tcol[t], w.ldt};
+    g[t].M = P; g[t].N = P; g[t].K = rows[t]; g[t].C = dW2[t];
+  }
+  const int tiles2 = 2 * ((P + BM - 1) / BM) * ((P + BN - 1) / BN);
+  if ((rc = launch_gemm(g, 2, np, choose_splits(tiles2, B), w.partial, 0, st))) return rc;
+  // 7. dz1 = (dY W2) * (h > 0)
+  for (int t = 0; t < 2; ++t) {
+    g[t] = GemmDesc{};
+    g[t].A = {w.dy_hi + (size_t)row0[t] * P, w.dy_lo + (size_t)row0[t] * P, P};
+    g[t].B = {w.w2t_hi[t], w.w2t_lo[t], P};
+    g[t].M = rows[t]; g[t].N = P; g[t].K = P; g[t].gate = s.h + (size_t)row0[t] * P;
+    g[t].C = w.dz1 + (size_t)row0[t] * P; g[t].ldc = P;
+    if (s.dxhat) {
+      g[t].C_hi = w.dz_hi + (size_t)row0[t] * P; g[t].C_lo = w.dz_lo + (size_t)row0[t] * P;
+    }
+    g[t].Ct_hi = w.dzt_hi + tcol[t]; g[t].Ct_lo = w.dzt_lo + tcol[t]; g[t].ldt = w.ldt;
+  }
+  if ((rc = launch_gemm(g, 2, np, 1, nullptr, 0, st))) return rc;
+  if ((rc = colsum2(w.dz1, rows[0], db1[0], w.dz1 + (size_t)row0[1] * P, rows[1], db1[1], P, P, 0, w.colsum, st)))
+    return rc;
+  // 8. dW1 = dz1^T x
+  for (int t = 0; t < 2; ++t) {
+    g[t] = GemmDesc{};
+    g[t].A = {w.dzt_hi + tcol[t], w.dzt_lo + tcol[t], w.ldt};
+    g[t].B = {w.xt_hi + tcol[t], w.xt_lo + tcol[t], w.ldt};
+    g[t].M = P; g[t].N = H; g[t].K = rows[t]; g[t].C = dW1[t];
+  }
+  const int tiles1 = 2 * ((P + BM - 1) / BM) * ((H + BN - 1) / BN);
+  if ((rc = launch_gemm(g, 2, np, choose_splits(tiles1, B), w.partial, 0, st))) return rc;
+  // 9. dxhat = dz1 W1 (only when the token tables train)
+  if (s.dxhat) {
+    for (int t = 0; t < 2; ++t) {
+      g[t] = GemmDesc{};
+      g[t].A = {w.dz_hi + (size_t)row0[t] * P, w.dz_lo + (size_t)row0[t] * P, P};
+      g[t].B = {w.w1t_hi[t], w.w1t_lo[t], P};
+      g[t].M = rows[t]; g[t].N = H; g[t].K = P; g[t].C = s.dxhat + (size_t)row0[t] * H; g[t].ldc = H;
+    }
+    if ((rc = launch_gemm(g, 2, np, 1, nullptr, 0, st))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace tt

@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(128)
         sp.dy_hi[row * P + c] = hi;
         sp.dy_lo[row * P + c] = lo;
         if (sp.dyt_hi) {
-          sp.dyt_hi[(size_t)c * sp.ldt + row] = hi;
-          sp.dyt_lo[(size_t)c * sp.ldt + row] = lo;
+          const size_t tcol = row + ((long long)row >= sp.t_split_row ? sp.t_shift : 0);
+          sp.dyt_hi[(size_t)c * sp.ldt + tcol] = hi;
+          sp.dyt_lo[(size_t)c * sp.ldt + tcol] = lo;
         }
       }
     }

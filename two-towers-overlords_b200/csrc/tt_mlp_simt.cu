@@ -86,7 +86,57 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   }
 }
 
+// two-stage column sums for up to two matrices per launch (query | document rows): slices of rows are summed
+// by separate CTAs into scratch[job][slice][N], then added in ascending slice order (deterministic)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X0, int M0,
+                                                             const float* __restrict__ X1, int M1, int N, long long ld,
+                                                             int S, float* __restrict__ scratch) {
+  __shared__ float s[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int job = blockIdx.z, slice = blockIdx.y;
+  const float* X = job ? X1 : X0;
+  const int M = job ? M1 : M0;
+  const int per = (M + S - 1) / S;
+  const int r0 = slice * per, r1 = min(M, r0 + per);
+  const int n = blockIdx.x * 32 + tx;
+  float sum = 0.f;
+  if (n < N)
+    for (int m = r0 + ty; m < r1; m += 8) sum += X[(size_t)m * ld + n];
+  s[ty][tx] = sum;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][tx];
+    scratch[((size_t)job * S + slice) * N + n] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ scratch, int S, int N,
+                                                           float* __restrict__ out0, float* __restrict__ out1,
+                                                           int accumulate) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int job = blockIdx.y;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int i = 0; i < S; ++i) t += scratch[((size_t)job * S + i) * N + n];
+  float* out = job ? out1 : out0;
+  out[n] = accumulate ? (out[n] + t) : t;
+}
+
 }  // namespace
+
+int colsum2(const float* X0, int M0, float* out0, const float* X1, int M1, float* out1, int N, long long ld,
+            int accumulate, float* scratch, cudaStream_t st) {
+  if (N <= 0) return 0;
+  const int njobs = X1 ? 2 : 1;
+  dim3 grid((N + 31) / 32, kColsumSlices, njobs);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(X0, M0, X1, M1, N, ld, kColsumSlices, scratch);
+  TT_LAUNCH_CHECK();
+  colsum_final_kernel<<<dim3((N + 255) / 256, njobs), 256, 0, st>>>(scratch, kColsumSlices, N, out0, out1, accumulate);
+  TT_LAUNCH_CHECK();
+  return 0;
+}
 
 int sgemm(const SgemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return 0;

@@ -202,11 +202,19 @@ __global__ void __launch_bounds__(kPoolThreads) pool_fwd_kernel(const PoolParams
       for (int c = 0; c < 4; ++c) split_bf16(xv[c], hi[c], lo[c]);
       *reinterpret_cast<uint2*>(p.x_hi + (size_t)row_out * H + tid * 4) = *reinterpret_cast<uint2*>(hi);
       *reinterpret_cast<uint2*>(p.x_lo + (size_t)row_out * H + tid * 4) = *reinterpret_cast<uint2*>(lo);
+      if (p.x_lo2) {
+        __nv_bfloat16 l2[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          l2[c] = __float2bfloat16_rn((xv[c] - __bfloat162float(hi[c])) - __bfloat162float(lo[c]));
+        *reinterpret_cast<uint2*>(p.x_lo2 + (size_t)row_out * H + tid * 4) = *reinterpret_cast<uint2*>(l2);
+      }
       if (p.xt_hi) {
+        const int tcol = row_out + (row_out >= p.t_split_row ? p.t_shift : 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          p.xt_hi[(size_t)(tid * 4 + c) * p.ldt + row_out] = hi[c];
-          p.xt_lo[(size_t)(tid * 4 + c) * p.ldt + row_out] = lo[c];
+          p.xt_hi[(size_t)(tid * 4 + c) * p.ldt + tcol] = hi[c];
+          p.xt_lo[(size_t)(tid * 4 + c) * p.ldt + tcol] = lo[c];
         }
       }
     }

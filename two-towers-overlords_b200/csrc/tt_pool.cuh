@@ -22,9 +22,13 @@ struct PoolParams {
   // optional operands for the tensor-core projection (bf16 hi/lo split)
   __nv_bfloat16* x_hi;   // [rows, H]
   __nv_bfloat16* x_lo;
+  __nv_bfloat16* x_lo2;  // nullable third term: xhat - hi - lo
   __nv_bfloat16* xt_hi;  // [H, ldt] transposed
   __nv_bfloat16* xt_lo;
   int ldt;
+  // column of row r in the transposed copies: r + (r >= t_split_row ? t_shift : 0) — lets the document rows
+  // start at a 64-aligned column so each tower's K range is its own TMA tensor
+  int t_split_row, t_shift;
 };
 
 int pool_fwd_launch(PoolParams p, int table_dtype, int H, cudaStream_t st);

@@ -23,6 +23,11 @@ int sgemm(const SgemmArgs& a, cudaStream_t st);
 // out[n] (+)= sum_m X[m*ld + n], fixed summation order
 int colsum(const float* X, int M, int N, long long ld, float* out, int accumulate, cudaStream_t st);
 
+// same sums for one or two matrices (X1 nullable) in two launches; scratch: 2 * kColsumSlices * N floats
+constexpr int kColsumSlices = 32;
+int colsum2(const float* X0, int M0, float* out0, const float* X1, int M1, float* out1, int N, long long ld,
+            int accumulate, float* scratch, cudaStream_t st);
+
 // fp32 strict-mode projection (tt_mlp_simt.cu)
 int mlp_fwd_fp32(const float* x, int M, int H, int P, const float* W1, const float* b1, const float* W2,
                  const float* b2, float* h, float* y, cudaStream_t st);
@@ -35,6 +40,7 @@ struct LossSplitOut {  // optional operands for the tensor-core backward: dY as 
   __nv_bfloat16 *dy_hi, *dy_lo;    // [3B, P]
   __nv_bfloat16 *dyt_hi, *dyt_lo;  // [P, ldt]
   int ldt;
+  int t_split_row, t_shift;        // transposed column of row r: r + (r >= t_split_row ? t_shift : 0)
 };
 int triplet_loss_fwd(const float* q, const float* p, const float* n, int B, int P, float margin, float inv_batch,
                      float* stats, float* loss, cudaStream_t st);
