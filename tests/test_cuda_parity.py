@@ -384,6 +384,67 @@ def test_scan_topk_fp32_vs_oracle(tt, Q, N, P, k):
     assert np.array_equal(top_i.cpu().numpy()[:3, : min(k, N)], ids[:, :k])
 
 
+@pytest.mark.parametrize("Q,N,P,k", [(1, 1000, 64, 10), (70, 4097, 384, 10), (200, 9950, 128, 16), (5, 7, 64, 10),
+                                     (64, 65, 512, 1), (300, 50_000, 384, 10), (129, 20_001, 72, 10)])
+def test_scan_topk_tensor_core_vs_oracle(tt, Q, N, P, k):
+    """tcgen05 scan: bf16 candidate generation + exact fp32 re-score must return the fp32 ranking."""
+    gen = torch.Generator().manual_seed(Q * N + 1)
+    Qe, De = torch.randn(Q, P, generator=gen), torch.randn(N, P, generator=gen)
+    Qn, Qb = tt.ops.l2_normalize_rows(Qe.to(DEV), want_bf16=True)
+    Dn, Db = tt.ops.l2_normalize_rows(De.to(DEV), want_bf16=True)
+    top_s, top_i = tt.ops.scan_topk(Qn, Dn, k=k, precision="bf16", Qb=Qb, Db=Db)
+    qn = Qe.double() / Qe.double().norm(dim=1, keepdim=True)
+    dn = De.double() / De.double().norm(dim=1, keepdim=True)
+    _check_topk(top_s.cpu().numpy(), top_i.cpu().numpy(), (qn @ dn.T).numpy(), k)
+    # and it is the same list the strict fp32 scan returns
+    ref_s, ref_i = tt.ops.scan_topk(Qn, Dn, k=k, precision="fp32")
+    same = (top_i == ref_i)
+    gaps_ok = same | ((top_s - ref_s).abs() < 1e-5)
+    assert bool(gaps_ok.all())
+
+
+def test_scan_tensor_core_exact_rescan_of_unproven_queries(tt, monkeypatch):
+    """With the error bound forced huge no candidate list can be proven complete: every query goes through the
+    listed fp32 re-scan, whose result must equal the strict fp32 scan bit for bit."""
+    gen = torch.Generator().manual_seed(77)
+    Q, N, P, k = 150, 6000, 128, 10
+    Qe, De = torch.randn(Q, P, generator=gen), torch.randn(N, P, generator=gen)
+    Qn, Qb = tt.ops.l2_normalize_rows(Qe.to(DEV), want_bf16=True)
+    Dn, Db = tt.ops.l2_normalize_rows(De.to(DEV), want_bf16=True)
+    ref_s, ref_i = tt.ops.scan_topk(Qn, Dn, k=k, precision="fp32", id_base=1000)
+    monkeypatch.setenv("TT_SCAN_EPS", "10")
+    top_s, top_i = tt.ops.scan_topk(Qn, Dn, k=k, precision="bf16", Qb=Qb, Db=Db, id_base=1000)
+    assert torch.equal(top_i, ref_i)
+    assert torch.allclose(top_s, ref_s, atol=1e-6)
+
+
+def test_scan_tensor_core_full_shard_properties(tt):
+    """1 M x 384 shard, 512 queries: planted neighbours are found, results are reproducible, and sharding the
+    corpus over 4 'GPUs' + merge gives the identical list."""
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    N, Q, P, k = 1_000_000, 512, 384, 10
+    De = torch.randn(N, P, generator=gen, device=DEV)
+    Qe = torch.randn(Q, P, generator=gen, device=DEV)
+    planted = torch.randint(0, N, (Q,), generator=gen, device=DEV)
+    De[planted] = Qe + 0.3 * torch.randn(Q, P, generator=gen, device=DEV)
+    shard = tt.retrieval.CorpusShard(De, precision="bf16")
+    s1, i1 = shard.search(Qe, k)
+    s2, i2 = shard.search(Qe, k)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    assert bool((i1[:, 0] == planted).all())
+    assert bool((s1[:, :-1] >= s1[:, 1:]).all())
+    parts = []
+    for r in range(4):
+        lo, hi = tt.retrieval.shard_bounds(N, 4, r)
+        parts.append(tt.retrieval.CorpusShard(De[lo:hi], id_base=lo, precision="bf16").search(Qe, k))
+    ms, mi = tt.ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi, i1)
+    # exactness of the scores: recompute the winners' cosines in float64
+    qn = torch.nn.functional.normalize(Qe.double(), dim=1)
+    dn = torch.nn.functional.normalize(De[i1[:, 0]].double(), dim=1)
+    assert float(((qn * dn).sum(1) - s1[:, 0].double()).abs().max()) < 1e-5
+
+
 def test_scan_ties_break_by_ascending_id(tt):
     De = torch.randn(50, 64)
     De[10] = De[3]

@@ -37,7 +37,15 @@ constexpr int SQ = 64, SD = 64, SK = 16;
 __global__ void __launch_bounds__(256)
     scan_topk_fp32_kernel(const float* __restrict__ Qn, const float* __restrict__ Dn, int Q, long long N, int P, int k,
                           long long docs_per_split, long long id_base, float* __restrict__ part_score,
-                          long long* __restrict__ part_id) {
+                          long long* __restrict__ part_id, const int* __restrict__ qlist,
+                          const int* __restrict__ qcount, int slot0) {
+  // indirect mode (qlist != null): this launch owns slots [slot0, slot0 + Q) of a device-side list of query rows
+  // (the re-scan of queries whose tensor-core candidates could not be proven complete); empty tiles exit at once
+  int n_slots = Q;
+  if (qlist) {
+    n_slots = min(Q, *qcount - slot0);
+    if ((int)blockIdx.y * SQ >= n_slots) return;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float (*As)[SQ + 4] = reinterpret_cast<float (*)[SQ + 4]>(smem_raw);
   float (*Bs)[SD + 4] = reinterpret_cast<float (*)[SD + 4]>(smem_raw + sizeof(float) * SK * (SQ + 4));
@@ -70,7 +78,8 @@ __global__ void __launch_bounds__(256)
         const int gq = q0 + r;
         const long long gd = d0 + r;
         const int gk = k0 + kk;
-        As[kk][r] = (gq < Q && gk < P) ? __ldg(Qn + (size_t)gq * P + gk) : 0.f;
+        const int qrow = (qlist && gq < n_slots) ? qlist[slot0 + gq] : gq;
+        As[kk][r] = (gq < n_slots && gk < P) ? __ldg(Qn + (size_t)qrow * P + gk) : 0.f;
         Bs[kk][r] = (gd < d_end && gk < P) ? __ldg(Dn + (size_t)gd * P + gk) : 0.f;
       }
       __syncthreads();
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int j = 0; j < 4; ++j) S[ty * 4 + i][tx * 4 + j] = acc[i][j];
     __syncthreads();
-    if (tid < SQ && q0 + tid < Q) {  // one thread per query walks its 64 scores in ascending doc id
+    if (tid < SQ && q0 + tid < n_slots) {  // one thread per query walks its 64 scores in ascending doc id
       float* ls = l_score + tid * k;
       long long* li = l_id + tid * k;
       const int nd = (int)min((long long)SD, d_end - d0);
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(256)
   }
   for (int i = tid; i < SQ * k; i += 256) {
     const int r = i / k, c = i % k;
-    if (q0 + r < Q) {
+    if (q0 + r < n_slots) {
       const size_t o = ((size_t)blockIdx.x * Q + q0 + r) * k + c;
       part_score[o] = l_score[i];
       part_id[o] = l_id[i];
@@ -127,10 +136,16 @@ __global__ void __launch_bounds__(256)
 // ---- merge G sorted partial lists per query ----------------------------------------------------------
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ ps, const long long* __restrict__ pi,
                                                          int G, int Q, int k, float* __restrict__ os,
-                                                         long long* __restrict__ oi) {
+                                                         long long* __restrict__ oi, const int* __restrict__ qlist,
+                                                         const int* __restrict__ qcount, int slot0) {
   const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= Q) return;
+  int qo = q;  // output row; indirect mode scatters slot (slot0 + q) back to its query row
+  if (qlist) {
+    if (slot0 + q >= *qcount) return;
+    qo = qlist[slot0 + q];
+  }
   float last_s = INFINITY;
   long long last_i = -1;
   const int total = G * k;
@@ -160,14 +175,14 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
       }
     }
     if (lane == 0) {
-      os[(size_t)q * k + r] = (bi >= 0) ? bs : -INFINITY;
-      oi[(size_t)q * k + r] = bi;
+      os[(size_t)qo * k + r] = (bi >= 0) ? bs : -INFINITY;
+      oi[(size_t)qo * k + r] = bi;
     }
     if (bi < 0) {
       for (int rr = r + 1; rr < k; ++rr)
         if (lane == 0) {
-          os[(size_t)q * k + rr] = -INFINITY;
-          oi[(size_t)q * k + rr] = -1;
+          os[(size_t)qo * k + rr] = -INFINITY;
+          oi[(size_t)qo * k + rr] = -1;
         }
       break;
     }
@@ -274,8 +289,38 @@ int scan_splits(int Q, long long N) {
 
 int topk_merge(const float* ps, const long long* pi, int G, int Q, int k, float* os, long long* oi, cudaStream_t st) {
   if (Q <= 0) return 0;
-  topk_merge_kernel<<<(Q + 7) / 8, 256, 0, st>>>(ps, pi, G, Q, k, os, oi);
+  topk_merge_kernel<<<(Q + 7) / 8, 256, 0, st>>>(ps, pi, G, Q, k, os, oi, nullptr, nullptr, 0);
   TT_LAUNCH_CHECK();
+  return 0;
+}
+
+// Exact fp32 re-scan of the query rows listed on the device (qlist[0 .. *qcount)), `cap` slots per round; results
+// overwrite top_score / top_id of exactly those rows.  ws: scan_listed_ws_bytes(cap, k).
+size_t scan_listed_ws_bytes(int cap, int k) {
+  return ws_round((size_t)kListedSplits * cap * k * 4) + ws_round((size_t)kListedSplits * cap * k * 8) + 512;
+}
+
+int scan_topk_fp32_listed(const float* Qn, const float* Dn, int Q, long long N, int P, int k, long long id_base,
+                          const int* qlist, const int* qcount, int cap, float* top_score, long long* top_id, void* ws,
+                          cudaStream_t st) {
+  if (Q <= 0 || N <= 0) return 0;
+  char* p = reinterpret_cast<char*>(ws);
+  float* ps = ws_take<float>(p, (size_t)kListedSplits * cap * k);
+  long long* pi = ws_take<long long>(p, (size_t)kListedSplits * cap * k);
+  int S = kListedSplits;
+  const long long max_splits = (N + SD - 1) / SD;
+  if (S > max_splits) S = (int)max_splits;
+  const long long per = ((N + S - 1) / S + SD - 1) / SD * SD;
+  const size_t smem = sizeof(float) * (SK * (SQ + 4 + SD + 4) + SQ * (SD + 1)) + (size_t)SQ * k * 4 + 8 + (size_t)SQ * k * 8;
+  TT_REQUIRE(smem <= 48 * 1024, "tt_scan_topk: k=%d too large for the fp32 scan", k);
+  for (int slot0 = 0; slot0 < Q; slot0 += cap) {  // later rounds find nothing to do unless > cap rows are listed
+    const int nq = min(cap, Q - slot0);
+    dim3 grid(S, (nq + SQ - 1) / SQ);
+    scan_topk_fp32_kernel<<<grid, 256, smem, st>>>(Qn, Dn, nq, N, P, k, per, id_base, ps, pi, qlist, qcount, slot0);
+    TT_LAUNCH_CHECK();
+    topk_merge_kernel<<<(nq + 7) / 8, 256, 0, st>>>(ps, pi, S, nq, k, top_score, top_id, qlist, qcount, slot0);
+    TT_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -291,7 +336,7 @@ int scan_topk_fp32(const float* Qn, const float* Dn, int Q, long long N, int P, 
   const size_t smem = sizeof(float) * (SK * (SQ + 4 + SD + 4) + SQ * (SD + 1)) + (size_t)SQ * k * 4 + 8 + (size_t)SQ * k * 8;
   TT_REQUIRE(smem <= 48 * 1024, "tt_scan_topk: k=%d too large for the fp32 scan", k);
   dim3 grid(S, (Q + SQ - 1) / SQ);
-  scan_topk_fp32_kernel<<<grid, 256, smem, st>>>(Qn, Dn, Q, N, P, k, per, id_base, ps, pi);
+  scan_topk_fp32_kernel<<<grid, 256, smem, st>>>(Qn, Dn, Q, N, P, k, per, id_base, ps, pi, nullptr, nullptr, 0);
   TT_LAUNCH_CHECK();
   return topk_merge(ps, pi, S, Q, k, top_score, top_id, st);
 }

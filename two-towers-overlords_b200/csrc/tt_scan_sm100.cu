@@ -1,0 +1,434 @@
+// Tensor-core corpus scan (TT_PREC_BF16 / TT_PREC_BF16X3 on tt_scan_topk): query x document dot products on
+// tcgen05.mma with a per-tile top-K' selection fused into the epilogue, so the score matrix lives only in TMEM.
+// Restates backend/training.py:297-304 (one `cosine_similarity` row + ranking per query) as a batched exhaustive scan.
+//
+//   1. scan_candidates_kernel — one CTA = 128 queries (bf16 tile resident in shared memory) x one document range.
+//      warp 0 streams 128-document x 64-k bf16 tiles by TMA through an mbarrier ring; warp 1 issues
+//      128x128x16 MMAs into a double-buffered TMEM accumulator; warps 2-5 read finished score tiles with
+//      tcgen05.ld (thread = query, columns = documents) and keep the KC best (approximate score, doc) per query
+//      in shared memory behind a register threshold — an insertion happens ~KC*ln(n/KC) times per query, so the
+//      epilogue is one compare per score and hides under the MMAs of the next tile.
+//   2. rescore_select_kernel — exact fp32 dot products (CUDA cores) of the S*KC candidates of each query, top-k by
+//      (score desc, id asc), plus a completeness proof: every non-candidate of split s has approximate score <=
+//      bound_s (the KC-th best of that split), and |approx - exact| <= eps for unit-norm rows, so the list is
+//      exact if max_s bound_s + eps < k-th exact score.  Queries that fail the proof are listed and re-scanned
+//      exactly in fp32 (scan_topk_fp32_listed), so the returned ids never depend on bf16 rounding.
+#include <stdlib.h>
+
+#include "tt_ptx.cuh"
+#include "tt_scan.cuh"
+#include "tt_sm100.cuh"
+#include "tt_tma.cuh"
+
+namespace tt {
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+using namespace ptx;
+
+constexpr int TQ = 128, TD = 128, BK = 64;
+constexpr int kScanThreads = 192;
+constexpr uint32_t kTileBytes = TD * BK * 2;  // 16 KB: one 128-row x 64-k bf16 tile (queries or documents)
+constexpr int kMaxKC = 64;
+constexpr int kMaxSplits = 148;
+constexpr size_t kSmemLimit = 227 * 1024;
+// |bf16(q).bf16(d) - q.d| <= |q - q~||d| + |q~||d - d~| <= 2^-9 + 2^-9 (1 + 2^-9) for rows of norm <= 1, plus the
+// tensor-core accumulation error (< 1e-6): a rigorous, deliberately loose bound
+constexpr float kScanEps = 4e-3f;
+
+struct alignas(64) ScanParams {
+  CUtensorMap q_map, d_map;
+  int Q, KB, KC, stages;
+  long long N, docs_per_split;
+  float* cand_s;   // [S, Q, KC] approximate scores (diagnostic / tie information)
+  int* cand_i;     // [S, Q, KC] local document index, -1 = empty
+  float* bound;    // [S, Q] KC-th best approximate score of the split, -inf if fewer than KC documents
+};
+
+__global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const __grid_constant__ ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ, split = blockIdx.y;
+  const long long d_beg = (long long)split * p.docs_per_split;
+  const long long d_end = min(d_beg + p.docs_per_split, p.N);
+  const int n_tiles = d_end > d_beg ? (int)((d_end - d_beg + TD - 1) / TD) : 0;
+  const int KB = p.KB, NS = p.stages, KC = p.KC;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* q_tile = smem;                               // KB x 16 KB
+  uint8_t* d_ring = smem + (size_t)KB * kTileBytes;     // NS x 16 KB
+  float* list_s = reinterpret_cast<float*>(d_ring + (size_t)NS * kTileBytes);  // [KC][128]
+  int* list_i = reinterpret_cast<int*>(list_s + KC * TQ);                      // [KC][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(list_i + KC * TQ);
+  uint64_t* empty = full + NS;
+  uint64_t* q_full = empty + NS;
+  uint64_t* tmem_full = q_full + 1;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(q_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&p.q_map);
+    prefetch_tensormap(&p.d_map);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * TD);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_tiles > 0) {  // ---- TMA producer ---------------------------------------------------------
+      mbar_arrive_expect_tx(q_full, (uint32_t)KB * kTileBytes);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(q_tile + (size_t)kb * kTileBytes, &p.q_map, q_full, kb * BK, q0);
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int d0 = (int)(d_beg + (long long)t * TD);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kTileBytes);
+          tma_load_2d(d_ring + (size_t)s * kTileBytes, &p.d_map, &full[s], kb * BK, d0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_tiles > 0) {  // ---- MMA issuer -------------------------------------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(TQ, TD);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(q_tile), r_addr = smem_u32(d_ring);
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&tmem_empty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(q_addr + (uint32_t)kb * kTileBytes);
+          const uint64_t db = make_smem_desc_sw128(r_addr + (uint32_t)s * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            mma_bf16(tmem_base + (uint32_t)(buf * TD), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {  // ---- epilogue: thread = query row, walks the 128 document scores of each finished tile ---------------
+    const int qd = warp & 3;
+    const int t_row = qd * 32 + lane;
+    const bool q_ok = q0 + t_row < p.Q;
+    float* ls = list_s + t_row;
+    int* li = list_i + t_row;
+    for (int j = 0; j < KC; ++j) {
+      ls[j * TQ] = -INFINITY;
+      li[j * TQ] = -1;
+    }
+    float thr = q_ok ? -INFINITY : INFINITY;  // rows past Q never insert
+    int minpos = 0;
+    int filled = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(&tmem_full[buf], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const int d0 = t * TD;  // local to the split
+      const int nd = (int)min((long long)TD, d_end - d_beg - d0);
+      for (int c = 0; c < TD / 16; ++c) {
+        float v[16];
+        tmem_ld16(tmem_base + (uint32_t)(buf * TD) + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 16), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (v[j] > thr) {  // thr = -inf while the list fills, +inf for rows past Q
+            const int dj = c * 16 + j;
+            if (dj < nd) {
+              // replace the current minimum (an empty slot while the list fills), then find the new minimum
+              ls[minpos * TQ] = v[j];
+              li[minpos * TQ] = d0 + dj;
+              if (filled < KC) ++filled;
+              float m = INFINITY;
+              int mp = 0;
+              for (int e = 0; e < KC; ++e) {
+                const float sv = ls[e * TQ];
+                if (sv < m) {
+                  m = sv;
+                  mp = e;
+                }
+              }
+              minpos = mp;
+              thr = (filled < KC) ? -INFINITY : m;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+    if (q_ok) {
+      const size_t o = ((size_t)split * p.Q + q0 + t_row) * KC;
+      const int base = (int)(d_beg);  // candidates are stored as indices local to the shard (0-based over N)
+      for (int j = 0; j < KC; ++j) {
+        const int id = li[j * TQ];
+        p.cand_s[o + j] = ls[j * TQ];
+        p.cand_i[o + j] = id < 0 ? -1 : base + id;
+      }
+      p.bound[(size_t)split * p.Q + q0 + t_row] = (filled < KC) ? -INFINITY : thr;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * TD);
+}
+
+__device__ __forceinline__ bool better(float s1, long long i1, float s2, long long i2) {
+  return s1 > s2 || (s1 == s2 && i1 < i2);
+}
+
+// one warp per query: exact fp32 scores of its candidates, top-k, completeness proof
+__global__ void __launch_bounds__(128)
+    rescore_select_kernel(const float* __restrict__ Qn, const float* __restrict__ Dn, const int* __restrict__ cand_i,
+                          const float* __restrict__ bound, int S, int Q, int KC, int P, int k, long long id_base,
+                          float eps, float* __restrict__ top_score, long long* __restrict__ top_id,
+                          int* __restrict__ flag) {
+  extern __shared__ float s_all[];  // [4 warps][C] scores, then [4][C] ids
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + warp;
+  if (q >= Q) return;
+  const int C = S * KC;
+  float* sc = s_all + (size_t)warp * C;
+  int* ids = reinterpret_cast<int*>(s_all + (size_t)4 * C) + (size_t)warp * C;
+  const float* qr = Qn + (size_t)q * P;
+  float bmax = -INFINITY;
+  for (int s = lane; s < S; s += 32) bmax = fmaxf(bmax, bound[(size_t)s * Q + q]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+  for (int c = 0; c < C; ++c) {
+    const int s = c / KC, j = c - s * KC;
+    const int id = cand_i[((size_t)s * Q + q) * KC + j];  // warp-uniform
+    float dot = 0.f;
+    if (id >= 0) {
+      const float* dr = Dn + (size_t)id * P;
+      for (int e = lane; e < P; e += 32) dot = fmaf(qr[e], dr[e], dot);
+      dot = warp_sum(dot);
+    }
+    if (lane == 0) {
+      sc[c] = dot;
+      ids[c] = id;
+    }
+  }
+  __syncwarp();
+  float last_s = INFINITY, kth = -INFINITY;
+  long long last_i = -1;
+  int found = 0;
+  for (int r = 0; r < k; ++r) {
+    float bs = -INFINITY;
+    long long bi = -1;
+    for (int c = lane; c < C; c += 32) {
+      const long long id = ids[c];
+      if (id < 0) continue;
+      const float s = sc[c];
+      const bool after = (r == 0) || better(last_s, last_i, s, id);
+      if (after && (bi < 0 || better(s, id, bs, bi))) {
+        bs = s;
+        bi = id;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float s2 = __shfl_xor_sync(0xffffffffu, bs, off);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (i2 >= 0 && (bi < 0 || better(s2, i2, bs, bi))) {
+        bs = s2;
+        bi = i2;
+      }
+    }
+    if (lane == 0) {
+      top_score[(size_t)q * k + r] = (bi >= 0) ? bs : -INFINITY;
+      top_id[(size_t)q * k + r] = (bi >= 0) ? bi + id_base : -1;
+    }
+    if (bi >= 0) {
+      last_s = bs;
+      last_i = bi;
+      kth = bs;
+      ++found;
+    } else {
+      last_s = -INFINITY;
+      last_i = -1;
+    }
+  }
+  // a document outside the candidate lists could only matter if its exact score can reach the k-th best
+  if (lane == 0) flag[q] = (found == k && bmax + eps >= kth) || (found < k && bmax > -INFINITY) ? 1 : 0;
+}
+
+// ordered compaction of the flagged query rows (single CTA: Q is at most a few hundred thousand)
+__global__ void __launch_bounds__(1024) compact_flags_kernel(const int* __restrict__ flag, int Q, int* __restrict__ qlist,
+                                                             int* __restrict__ qcount) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < Q; q0 += 1024) {
+    const int q = q0 + threadIdx.x;
+    const bool f = q < Q && flag[q] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (f) qlist[off + __popc(bal & ((1u << lane) - 1u))] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *qcount = s_base;
+}
+
+struct ScanPlan {
+  int n_qtiles, S, KC, KB, stages, cap;
+  long long docs_per_split;
+  size_t smem;
+};
+
+int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
+  ScanPlan pl{};
+  pl.n_qtiles = (Q + TQ - 1) / TQ;
+  pl.KB = (P + BK - 1) / BK;
+  const long long tiles = (N + TD - 1) / TD;
+  // document splits: fill the machine when there are few query tiles, otherwise aim at whole waves
+  int S = 1;
+  const int sms = sm_count();
+  if (pl.n_qtiles < 2 * sms) {
+    S = (2 * sms + pl.n_qtiles - 1) / pl.n_qtiles;
+    if (pl.n_qtiles == 1) S = sms;
+  } else {
+    // smallest S <= 8 that leaves the last wave at least 85 % full
+    for (int c = 1; c <= 8; ++c) {
+      const long long ctas = (long long)pl.n_qtiles * c;
+      const double waves = (double)ctas / sms;
+      if (waves / (double)((ctas + sms - 1) / sms) >= 0.85) { S = c; break; }
+      S = c;
+    }
+  }
+  if (S > tiles) S = (int)tiles;
+  if (S > kMaxSplits) S = kMaxSplits;
+  if (S < 1) S = 1;
+  pl.docs_per_split = ((tiles + S - 1) / S) * TD;
+  S = (int)((N + pl.docs_per_split - 1) / pl.docs_per_split);
+  pl.S = S;
+  int kc = S >= 6 ? 16 : (S >= 3 ? 32 : 64);
+  while (kc < k + 6 && kc < kMaxKC) kc *= 2;
+  pl.KC = kc;
+  const size_t fixed = 1024 + 512 + (size_t)pl.KB * kTileBytes + (size_t)kc * TQ * 8;
+  int stages = (int)((kSmemLimit - fixed) / kTileBytes);
+  if (stages > 8) stages = 8;
+  pl.stages = stages;
+  pl.smem = fixed + (size_t)stages * kTileBytes;
+  pl.cap = Q < 8192 ? Q : 8192;
+  *out = pl;
+  return 0;
+}
+
+float scan_eps() {
+  const char* e = getenv("TT_SCAN_EPS");  // test hook: a huge value forces every query through the exact re-scan
+  return e ? (float)atof(e) : kScanEps;
+}
+
+struct ScanWs {
+  float* cand_s;
+  int* cand_i;
+  float* bound;
+  int *flag, *qlist, *qcount;
+  void* listed;
+};
+
+size_t carve_scan(char* base, const ScanPlan& pl, int Q, int k, ScanWs* out) {
+  char* p = base;
+  ScanWs w{};
+  w.cand_s = ws_take<float>(p, (size_t)pl.S * Q * pl.KC);
+  w.cand_i = ws_take<int>(p, (size_t)pl.S * Q * pl.KC);
+  w.bound = ws_take<float>(p, (size_t)pl.S * Q);
+  w.flag = ws_take<int>(p, Q);
+  w.qlist = ws_take<int>(p, Q);
+  w.qcount = ws_take<int>(p, 64);
+  w.listed = ws_take<char>(p, scan_listed_ws_bytes(pl.cap, k));
+  if (out) *out = w;
+  return (size_t)(p - base) + 256;
+}
+
+}  // namespace
+
+size_t scan_sm100_ws_bytes(int Q, long long N, int P, int k) {
+  ScanPlan pl;
+  make_plan(Q, N, P, k, &pl);
+  return carve_scan(nullptr, pl, Q, k, nullptr);
+}
+
+int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void* Db, int Q, long long N, int P, int k,
+                    long long id_base, float* top_score, long long* top_id, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  TT_REQUIRE(P % 8 == 0 && P <= 512, "tt_scan_topk: the tensor-core scan needs P %% 8 == 0 and P <= 512 (P=%d)", P);
+  TT_REQUIRE(k <= 32, "tt_scan_topk: the tensor-core scan keeps at most 32 results per query (k=%d)", k);
+  TT_REQUIRE(N < (1ll << 31), "tt_scan_topk: a shard holds at most 2^31 documents");
+  ScanPlan pl;
+  make_plan(Q, N, P, k, &pl);
+  TT_REQUIRE(pl.stages >= 2, "tt_scan_topk: not enough shared memory for P=%d", P);
+  TT_REQUIRE(ws_bytes >= carve_scan(nullptr, pl, Q, k, nullptr), "tt_scan_topk: workspace too small");
+  ScanWs w;
+  carve_scan(reinterpret_cast<char*>(ws), pl, Q, k, &w);
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    TT_CUDA(cudaFuncSetAttribute(scan_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_done = true;
+  }
+  ScanParams sp{};
+  int rc;
+  if ((rc = make_map_bf16_kmajor(&sp.q_map, Qb, Q, P, P, TQ))) return rc;
+  if ((rc = make_map_bf16_kmajor(&sp.d_map, Db, (uint64_t)N, P, P, TD))) return rc;
+  sp.Q = Q; sp.KB = pl.KB; sp.KC = pl.KC; sp.stages = pl.stages;
+  sp.N = N; sp.docs_per_split = pl.docs_per_split;
+  sp.cand_s = w.cand_s; sp.cand_i = w.cand_i; sp.bound = w.bound;
+  scan_candidates_kernel<<<dim3(pl.n_qtiles, pl.S), kScanThreads, pl.smem, st>>>(sp);
+  TT_LAUNCH_CHECK();
+
+  const int C = pl.S * pl.KC;
+  const size_t rs_smem = (size_t)4 * C * 8;
+  TT_REQUIRE(rs_smem <= 200 * 1024, "tt_scan_topk: candidate set too large (%d per query)", C);
+  static size_t rs_attr = 0;
+  if (rs_smem > 48 * 1024 && rs_smem > rs_attr) {
+    TT_CUDA(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    rs_attr = 200 * 1024;
+  }
+  rescore_select_kernel<<<(Q + 3) / 4, 128, rs_smem, st>>>(Qn, Dn, w.cand_i, w.bound, pl.S, Q, pl.KC, P, k, id_base,
+                                                          scan_eps(), top_score, top_id, w.flag);
+  TT_LAUNCH_CHECK();
+  compact_flags_kernel<<<1, 1024, 0, st>>>(w.flag, Q, w.qlist, w.qcount);
+  TT_LAUNCH_CHECK();
+  return scan_topk_fp32_listed(Qn, Dn, Q, N, P, k, id_base, w.qlist, w.qcount, pl.cap, top_score, top_id, w.listed, st);
+}
+
+}  // namespace tt
