@@ -328,6 +328,12 @@ def run_b200(args):
                "sample": f"{info['steps']} fp32 steps of {info['batch']} triplets in {info['seconds']} s "
                          f"(oracle/two_towers_oracle.train_step, torch CPU, {info['cores']} threads)"}
 
+    scan = None
+    if not args.no_scan:
+        del trainer, model
+        torch.cuda.empty_cache()
+        scan = run_scan(dev, world, rank, args.scan_docs, args.scan_queries, HIDDEN, args.scan_passes)
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -338,10 +344,114 @@ def run_b200(args):
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": launches_per_step * K, "gpu_launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "loss_after": loss_after,
+            "loss_after": loss_after, "scan": scan,
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# corpus scan (BASELINE.json configs[4]): sharded exhaustive top-10 + NDCG@10
+# --------------------------------------------------------------------------------------------------
+def run_scan(dev, world, rank, n_docs, n_queries, P, passes, precision="bf16"):
+    """Strong scaling: the corpus is split over the ranks, every rank scores all queries against its shard, one
+    all-gather of the [Q,10] lists, merge, NDCG@10.  Returns the `scan` object of the JSON line."""
+    import torch.distributed as dist
+
+    from two_towers_overlords_b200 import ops, retrieval
+
+    hbm_peak, tensor_peak, peak_kind = peaks()
+    lo, hi = retrieval.shard_bounds(n_docs, world, rank)
+    n_local = hi - lo
+    g = torch.Generator(device=dev).manual_seed(7)          # same stream on every rank: global corpus, own slice
+    gq = torch.Generator(device=dev).manual_seed(8)
+    Qe = torch.randn(n_queries, P, generator=gq, device=dev)
+    # relevant sets: 1..10 documents per query, planted as query + noise so that NDCG@10 is non-trivial
+    gr = torch.Generator(device=dev).manual_seed(9)
+    n_rel = torch.randint(1, 11, (n_queries,), generator=gr, device=dev)
+    owner = torch.repeat_interleave(torch.arange(n_queries, device=dev), n_rel)
+    rel_ids = torch.randperm(n_docs, generator=gr, device=dev)[: owner.numel()]
+    noise = 1.0 + 5.0 * torch.rand(owner.numel(), generator=gr, device=dev)
+    De = torch.empty(n_local, P, device=dev)
+    chunk = 1 << 20
+    for s0 in range(0, n_docs, chunk):                       # draw the global corpus chunk by chunk, keep my rows
+        blk = torch.randn(min(chunk, n_docs - s0), P, generator=g, device=dev)
+        a, b = max(lo, s0), min(hi, s0 + blk.shape[0])
+        if a < b:
+            De[a - lo: b - lo] = blk[a - s0: b - s0]
+    mine = (rel_ids >= lo) & (rel_ids < hi)
+    gn = torch.Generator(device=dev).manual_seed(10)
+    plant_noise = torch.randn(owner.numel(), P, generator=gn, device=dev)
+    De[rel_ids[mine] - lo] = Qe[owner[mine]] + noise[mine, None] * plant_noise[mine]
+    del plant_noise
+    order = torch.argsort(owner * n_docs + rel_ids)
+    rel_csr = (torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(n_rel, 0)]), rel_ids[order].contiguous())
+    shard = retrieval.CorpusShard(De, id_base=lo, precision=precision)
+    del De
+    torch.cuda.synchronize()
+
+    def one_pass(q):
+        return retrieval.retrieve_and_score(shard, q, rel_csr, k=10, world_size=world)
+
+    def timed(fn, n):
+        fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    lib = ops.N.load()
+    n0 = lib.tt_launch_count()
+    ms_full, (top_s, top_i, ndcg) = timed(lambda: one_pass(Qe), passes)
+    launches = (lib.tt_launch_count() - n0) // (passes + 1)
+    # end to end: query embeddings start in pinned host memory, top-10 ids + NDCG come back to the host
+    Qh = Qe.cpu().pin_memory()
+    ids_h = torch.empty(n_queries, 10, dtype=torch.int64).pin_memory()
+    ndcg_h = torch.empty(n_queries, dtype=torch.float64).pin_memory()
+
+    def e2e_pass():
+        q = Qh.to(dev, non_blocking=True)
+        _, ti, nd = one_pass(q)
+        ids_h.copy_(ti, non_blocking=True)
+        ndcg_h.copy_(nd, non_blocking=True)
+        return None
+
+    ms_e2e, _ = timed(e2e_pass, passes)
+    # streaming regime of the reference's own eval (few queries per pass, training.py:244): one 128-query tile
+    q_small = Qe[:128].contiguous()
+    ms_small, _ = timed(lambda: shard.search(q_small, 10), 10)
+    flops = 2.0 * n_queries * n_local * P
+    stream_bytes = n_local * P * 2.0
+    return {
+        "metric": "top10_queries_per_sec", "value": n_queries / (ms_full * 1e-3), "unit": "queries/s", "scaling": "strong",
+        "config": {"workload": "configs[4] corpus scan: synthetic unit-norm passages x 384-d, top-10 + NDCG@10",
+                   "n_docs": n_docs, "docs_per_gpu": n_local, "n_queries": n_queries, "dim": P, "k": 10,
+                   "precision": f"{precision} tensor-core candidates + exact fp32 re-score", "passes": passes},
+        "ms_per_pass": ms_full, "mean_ndcg_10": float(ndcg.mean().item()),
+        "e2e": {"value": n_queries / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_pass": Qh.numel() * 4,
+                "d2h_bytes_per_pass": ids_h.numel() * 8 + ndcg_h.numel() * 8, "ms_per_pass": ms_e2e},
+        "gpu_launches_per_pass": int(launches),
+        "roofline_batched": {"bound": "tensor", "achieved": flops / (ms_full * 1e-3) / 1e12, "peak": tensor_peak,
+                             "peak_kind": peak_kind, "unit": "TFLOP/s",
+                             "frac": flops / (ms_full * 1e-3) / 1e12 / tensor_peak,
+                             "note": "whole pass (scan + re-score + merge + NDCG); 2*Q*N_local*P flops"},
+        "roofline_streaming": {"bound": "hbm", "queries": 128, "achieved": stream_bytes / (ms_small * 1e-3) / 1e9,
+                               "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s",
+                               "frac": stream_bytes / (ms_small * 1e-3) / 1e9 / hbm_peak, "ms_per_pass": ms_small,
+                               "note": "one 128-query tile against the whole bf16 shard (N_local*P*2 bytes), "
+                                       "including re-score; passes/s = the reference's per-query eval regime"},
+    }
 
 
 def main():
@@ -355,6 +465,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-scan", action="store_true")
+    ap.add_argument("--scan-docs", type=int, default=8_800_000)
+    ap.add_argument("--scan-queries", type=int, default=100_000)
+    ap.add_argument("--scan-passes", type=int, default=2)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

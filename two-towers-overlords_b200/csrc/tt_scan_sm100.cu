@@ -30,7 +30,8 @@ using namespace ptx;
 constexpr int TQ = 128, TD = 128, BK = 64;
 constexpr int kScanThreads = 192;
 constexpr uint32_t kTileBytes = TD * BK * 2;  // 16 KB: one 128-row x 64-k bf16 tile (queries or documents)
-constexpr int kMaxKC = 64;
+constexpr int kMaxKC = 48;
+constexpr int kSlack = 32;  // append room beyond KC between two compactions (>= 16: one tcgen05.ld chunk)
 constexpr int kMaxSplits = 148;
 constexpr size_t kSmemLimit = 227 * 1024;
 // |bf16(q).bf16(d) - q.d| <= |q - q~||d| + |q~||d - d~| <= 2^-9 + 2^-9 (1 + 2^-9) for rows of norm <= 1, plus the
@@ -59,9 +60,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* q_tile = smem;                               // KB x 16 KB
   uint8_t* d_ring = smem + (size_t)KB * kTileBytes;     // NS x 16 KB
-  float* list_s = reinterpret_cast<float*>(d_ring + (size_t)NS * kTileBytes);  // [KC][128]
-  int* list_i = reinterpret_cast<int*>(list_s + KC * TQ);                      // [KC][128]
-  uint64_t* full = reinterpret_cast<uint64_t*>(list_i + KC * TQ);
+  float* list_s = reinterpret_cast<float*>(d_ring + (size_t)NS * kTileBytes);  // [KC + kSlack][128]
+  int* list_i = reinterpret_cast<int*>(list_s + (KC + kSlack) * TQ);           // [KC + kSlack][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(list_i + (KC + kSlack) * TQ);
   uint64_t* empty = full + NS;
   uint64_t* q_full = empty + NS;
   uint64_t* tmem_full = q_full + 1;   // [2]
@@ -134,18 +135,45 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       }
     }
   } else {  // ---- epilogue: thread = query row, walks the 128 document scores of each finished tile ---------------
+    // Per query an append buffer of CAP = KC + kSlack entries behind a register threshold: a score above the
+    // threshold is appended (two shared stores); when any lane of the warp runs out of room the whole warp
+    // compacts together — a selection pass keeps each lane's KC best and raises its threshold to the KC-th.
+    // The threshold only ever rises, so every document not in the final list scored <= the final threshold.
     const int qd = warp & 3;
     const int t_row = qd * 32 + lane;
     const bool q_ok = q0 + t_row < p.Q;
+    const int CAP = KC + kSlack;
     float* ls = list_s + t_row;
     int* li = list_i + t_row;
-    for (int j = 0; j < KC; ++j) {
-      ls[j * TQ] = -INFINITY;
-      li[j * TQ] = -1;
-    }
-    float thr = q_ok ? -INFINITY : INFINITY;  // rows past Q never insert
-    int minpos = 0;
-    int filled = 0;
+    float thr = q_ok ? -INFINITY : INFINITY;  // rows past Q never append
+    int cnt = 0;
+    auto compact = [&]() {
+      const int nmax = __reduce_max_sync(0xffffffffu, cnt);
+      const int rounds = min(KC, nmax);
+      for (int r = 0; r < rounds; ++r) {
+        float best = -INFINITY;
+        int bp = r;
+        for (int e = r; e < nmax; ++e) {
+          const float sv = (e < cnt) ? ls[e * TQ] : -INFINITY;
+          if (sv > best) {
+            best = sv;
+            bp = e;
+          }
+        }
+        if (r < cnt && bp != r) {
+          const float s0 = ls[r * TQ];
+          const int i0 = li[r * TQ];
+          ls[r * TQ] = best;
+          li[r * TQ] = li[bp * TQ];
+          ls[bp * TQ] = s0;
+          li[bp * TQ] = i0;
+        }
+      }
+      if (cnt >= KC) {
+        cnt = KC;
+        thr = ls[(KC - 1) * TQ];
+      }
+    };
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       mbar_wait(&tmem_full[buf], (uint32_t)(t >> 1) & 1u);
@@ -155,43 +183,36 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       for (int c = 0; c < TD / 16; ++c) {
         float v[16];
         tmem_ld16(tmem_base + (uint32_t)(buf * TD) + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 16), v);
+        float m = v[0];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (v[j] > thr) {  // thr = -inf while the list fills, +inf for rows past Q
+        for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
+        if (m > thr) {  // rare once the threshold has settled
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
             const int dj = c * 16 + j;
-            if (dj < nd) {
-              // replace the current minimum (an empty slot while the list fills), then find the new minimum
-              ls[minpos * TQ] = v[j];
-              li[minpos * TQ] = d0 + dj;
-              if (filled < KC) ++filled;
-              float m = INFINITY;
-              int mp = 0;
-              for (int e = 0; e < KC; ++e) {
-                const float sv = ls[e * TQ];
-                if (sv < m) {
-                  m = sv;
-                  mp = e;
-                }
-              }
-              minpos = mp;
-              thr = (filled < KC) ? -INFINITY : m;
+            if (v[j] > thr && dj < nd) {
+              ls[cnt * TQ] = v[j];
+              li[cnt * TQ] = d0 + dj;
+              ++cnt;
             }
           }
         }
+        if (__any_sync(0xffffffffu, cnt > CAP - 16)) compact();  // warp-uniform: no lane can overflow next chunk
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
+    compact();
     if (q_ok) {
       const size_t o = ((size_t)split * p.Q + q0 + t_row) * KC;
       const int base = (int)(d_beg);  // candidates are stored as indices local to the shard (0-based over N)
       for (int j = 0; j < KC; ++j) {
-        const int id = li[j * TQ];
-        p.cand_s[o + j] = ls[j * TQ];
-        p.cand_i[o + j] = id < 0 ? -1 : base + id;
+        const bool have = j < cnt;
+        p.cand_s[o + j] = have ? ls[j * TQ] : -INFINITY;
+        p.cand_i[o + j] = have ? base + li[j * TQ] : -1;
       }
-      p.bound[(size_t)split * p.Q + q0 + t_row] = (filled < KC) ? -INFINITY : thr;
+      p.bound[(size_t)split * p.Q + q0 + t_row] = thr;  // -inf until KC documents have been seen
     }
   }
   tc_fence_before();
@@ -203,39 +224,51 @@ __device__ __forceinline__ bool better(float s1, long long i1, float s2, long lo
   return s1 > s2 || (s1 == s2 && i1 < i2);
 }
 
-// one warp per query: exact fp32 scores of its candidates, top-k, completeness proof
+// exact fp32 dot products of the candidates: one warp per (query, group of kGroup candidates), query row in registers
+constexpr int kGroup = 32;
 __global__ void __launch_bounds__(128)
-    rescore_select_kernel(const float* __restrict__ Qn, const float* __restrict__ Dn, const int* __restrict__ cand_i,
-                          const float* __restrict__ bound, int S, int Q, int KC, int P, int k, long long id_base,
-                          float eps, float* __restrict__ top_score, long long* __restrict__ top_id,
-                          int* __restrict__ flag) {
-  extern __shared__ float s_all[];  // [4 warps][C] scores, then [4][C] ids
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 4 + warp;
-  if (q >= Q) return;
+    rescore_kernel(const float* __restrict__ Qn, const float* __restrict__ Dn, const int* __restrict__ cand_i, int S,
+                   int Q, int KC, int P, float* __restrict__ exact) {
   const int C = S * KC;
-  float* sc = s_all + (size_t)warp * C;
-  int* ids = reinterpret_cast<int*>(s_all + (size_t)4 * C) + (size_t)warp * C;
+  const int groups = (C + kGroup - 1) / kGroup;
+  const long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)Q * groups) return;
+  const int q = (int)(w / groups), g = (int)(w - (long long)q * groups);
+  float qv[16];  // P <= 512
   const float* qr = Qn + (size_t)q * P;
-  float bmax = -INFINITY;
-  for (int s = lane; s < S; s += 32) bmax = fmaxf(bmax, bound[(size_t)s * Q + q]);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-  for (int c = 0; c < C; ++c) {
+  for (int i = 0; i < 16; ++i) qv[i] = (lane + 32 * i < P) ? qr[lane + 32 * i] : 0.f;
+  const int c1 = min(C, (g + 1) * kGroup);
+  for (int c = g * kGroup; c < c1; ++c) {
     const int s = c / KC, j = c - s * KC;
     const int id = cand_i[((size_t)s * Q + q) * KC + j];  // warp-uniform
     float dot = 0.f;
     if (id >= 0) {
       const float* dr = Dn + (size_t)id * P;
-      for (int e = lane; e < P; e += 32) dot = fmaf(qr[e], dr[e], dot);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (lane + 32 * i < P) dot = fmaf(qv[i], __ldg(dr + lane + 32 * i), dot);
       dot = warp_sum(dot);
     }
-    if (lane == 0) {
-      sc[c] = dot;
-      ids[c] = id;
-    }
+    if (lane == 0) exact[(size_t)q * C + c] = dot;
   }
-  __syncwarp();
+}
+
+// one warp per query: top-k of the exactly scored candidates + completeness proof
+__global__ void __launch_bounds__(128)
+    select_kernel(const float* __restrict__ exact, const int* __restrict__ cand_i, const float* __restrict__ bound, int S,
+                  int Q, int KC, int k, long long id_base, float eps, float* __restrict__ top_score,
+                  long long* __restrict__ top_id, int* __restrict__ flag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + warp;
+  if (q >= Q) return;
+  const int C = S * KC;
+  const float* sc = exact + (size_t)q * C;
+  float bmax = -INFINITY;
+  for (int s = lane; s < S; s += 32) bmax = fmaxf(bmax, bound[(size_t)s * Q + q]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
   float last_s = INFINITY, kth = -INFINITY;
   long long last_i = -1;
   int found = 0;
@@ -243,12 +276,13 @@ __global__ void __launch_bounds__(128)
     float bs = -INFINITY;
     long long bi = -1;
     for (int c = lane; c < C; c += 32) {
-      const long long id = ids[c];
+      const int s = c / KC, j = c - s * KC;
+      const long long id = cand_i[((size_t)s * Q + q) * KC + j];
       if (id < 0) continue;
-      const float s = sc[c];
-      const bool after = (r == 0) || better(last_s, last_i, s, id);
-      if (after && (bi < 0 || better(s, id, bs, bi))) {
-        bs = s;
+      const float sv = sc[c];
+      const bool after = (r == 0) || better(last_s, last_i, sv, id);
+      if (after && (bi < 0 || better(sv, id, bs, bi))) {
+        bs = sv;
         bi = id;
       }
     }
@@ -276,7 +310,7 @@ __global__ void __launch_bounds__(128)
     }
   }
   // a document outside the candidate lists could only matter if its exact score can reach the k-th best
-  if (lane == 0) flag[q] = (found == k && bmax + eps >= kth) || (found < k && bmax > -INFINITY) ? 1 : 0;
+  if (lane == 0) flag[q] = ((found == k && bmax + eps >= kth) || (found < k && bmax > -INFINITY)) ? 1 : 0;
 }
 
 // ordered compaction of the flagged query rows (single CTA: Q is at most a few hundred thousand)
@@ -339,11 +373,17 @@ int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
   pl.docs_per_split = ((tiles + S - 1) / S) * TD;
   S = (int)((N + pl.docs_per_split - 1) / pl.docs_per_split);
   pl.S = S;
-  int kc = S >= 6 ? 16 : (S >= 3 ? 32 : 64);
-  while (kc < k + 6 && kc < kMaxKC) kc *= 2;
+  int kc = S >= 6 ? 16 : (S >= 3 ? 32 : kMaxKC);
+  while (kc < k + 6 && kc < kMaxKC) kc += 16;
+  // shared memory: resident query tile + candidate buffers + at least 3 document stages (wide P trades KC for stages)
+  size_t fixed = 0;
+  int stages = 0;
+  for (;; kc -= 16) {
+    fixed = 1024 + 512 + (size_t)pl.KB * kTileBytes + (size_t)(kc + kSlack) * TQ * 8;
+    stages = fixed < kSmemLimit ? (int)((kSmemLimit - fixed) / kTileBytes) : 0;
+    if (stages >= 3 || kc - 16 < k + 6 || kc <= 16) break;
+  }
   pl.KC = kc;
-  const size_t fixed = 1024 + 512 + (size_t)pl.KB * kTileBytes + (size_t)kc * TQ * 8;
-  int stages = (int)((kSmemLimit - fixed) / kTileBytes);
   if (stages > 8) stages = 8;
   pl.stages = stages;
   pl.smem = fixed + (size_t)stages * kTileBytes;
@@ -358,6 +398,7 @@ float scan_eps() {
 }
 
 struct ScanWs {
+  float* exact;
   float* cand_s;
   int* cand_i;
   float* bound;
@@ -368,6 +409,7 @@ struct ScanWs {
 size_t carve_scan(char* base, const ScanPlan& pl, int Q, int k, ScanWs* out) {
   char* p = base;
   ScanWs w{};
+  w.exact = ws_take<float>(p, (size_t)pl.S * Q * pl.KC);
   w.cand_s = ws_take<float>(p, (size_t)pl.S * Q * pl.KC);
   w.cand_i = ws_take<int>(p, (size_t)pl.S * Q * pl.KC);
   w.bound = ws_take<float>(p, (size_t)pl.S * Q);
@@ -416,15 +458,11 @@ int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void
   TT_LAUNCH_CHECK();
 
   const int C = pl.S * pl.KC;
-  const size_t rs_smem = (size_t)4 * C * 8;
-  TT_REQUIRE(rs_smem <= 200 * 1024, "tt_scan_topk: candidate set too large (%d per query)", C);
-  static size_t rs_attr = 0;
-  if (rs_smem > 48 * 1024 && rs_smem > rs_attr) {
-    TT_CUDA(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    rs_attr = 200 * 1024;
-  }
-  rescore_select_kernel<<<(Q + 3) / 4, 128, rs_smem, st>>>(Qn, Dn, w.cand_i, w.bound, pl.S, Q, pl.KC, P, k, id_base,
-                                                          scan_eps(), top_score, top_id, w.flag);
+  const long long warps = (long long)Q * ((C + kGroup - 1) / kGroup);
+  rescore_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(Qn, Dn, w.cand_i, pl.S, Q, pl.KC, P, w.exact);
+  TT_LAUNCH_CHECK();
+  select_kernel<<<(Q + 3) / 4, 128, 0, st>>>(w.exact, w.cand_i, w.bound, pl.S, Q, pl.KC, k, id_base, scan_eps(), top_score,
+                                             top_id, w.flag);
   TT_LAUNCH_CHECK();
   compact_flags_kernel<<<1, 1024, 0, st>>>(w.flag, Q, w.qlist, w.qcount);
   TT_LAUNCH_CHECK();
