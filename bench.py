@@ -188,6 +188,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from two_towers_overlords_b200 import TwoTowersModel, _native
