@@ -156,7 +156,8 @@ typedef struct tt_step_args {
   float *dtable_q, *dtable_d; /* nullable                            */
   int* err_flag;     /* nullable                                     */
   int precision;
-  void* ws; size_t ws_bytes;  /* >= tt_step_ws_bytes(...)            */
+  void* ws; size_t ws_bytes;  /* >= tt_step_ws_bytes(...); zero-fill it once before its first use (it holds an
+                                 arrival counter that every call leaves at zero again)                        */
 } tt_step_args;
 size_t tt_step_ws_bytes(int B, int Lq, int Ld, int H, int P, int vocab, int precision,
                         int train_table);

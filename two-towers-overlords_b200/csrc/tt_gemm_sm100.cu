@@ -24,7 +24,7 @@ using bf16 = __nv_bfloat16;
 using namespace ptx;
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 6;
+constexpr int kStages = 3;  // 3 x 32 KB: two CTAs per SM, so one CTA's epilogue overlaps the other's main loop
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -47,7 +47,7 @@ struct alignas(64) GemmParams {
   int ngroups, splits, n_pairs, pad;
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gi = blockIdx.z / p.splits, split = blockIdx.z - gi * p.splits;
@@ -197,9 +197,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
-// out[i] = (accumulate ? out[i] : 0) + sum_z partial[z][i], z ascending: fixed order, no atomics
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n,
-                                                            float* __restrict__ out, int accumulate) {
+// out[i] = (accumulate ? out[i] : 0) + sum_z partial[z][i], z ascending: fixed order, no atomics.  blockIdx.y = group.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial0, float* __restrict__ out0,
+                                                            size_t n0, const float* __restrict__ partial1,
+                                                            float* __restrict__ out1, size_t n1, int splits,
+                                                            int accumulate) {
+  const float* partial = blockIdx.y ? partial1 : partial0;
+  float* out = blockIdx.y ? out1 : out0;
+  const size_t n = blockIdx.y ? n1 : n0;
   const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (i >= n) return;
   float4 acc = accumulate ? *reinterpret_cast<const float4*>(out + i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -210,46 +215,59 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   *reinterpret_cast<float4*>(out + i) = acc;
 }
 
-// fp32 [R, C] (pitch ld) -> bf16 hi/lo [R, C] and, optionally, transposed hi/lo [C, ldt] (column = row index + tcol0)
-__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ X, int R, int C, long long ld,
-                                                              bf16* __restrict__ hi, bf16* __restrict__ lo,
-                                                              bf16* __restrict__ lo2, bf16* __restrict__ thi,
-                                                              bf16* __restrict__ tlo, int ldt, int tcol0) {
+// fp32 [R, C] (pitch ld) -> bf16 terms hi/lo[/lo2] [R, C] and, optionally, transposed hi/lo [C, ldt] (column = row
+// index + tcol0).  Up to 4 matrices per launch (blockIdx.z = job): all projection weights of a step in one go.
+struct SplitJob {
+  const float* X;
+  int R, C;
+  long long ld;
+  bf16 *hi, *lo, *lo2, *thi, *tlo;
+  int ldt, tcol0;
+};
+struct SplitJobs {
+  SplitJob j[4];
+};
+
+__global__ void __launch_bounds__(256) split_transpose_kernel(const SplitJobs jobs) {
   __shared__ bf16 s_hi[32][33], s_lo[32][33];
+  const SplitJob& J = jobs.j[blockIdx.z];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  if (r0 >= J.R || c0 >= J.C) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + ty + i * 8, c = c0 + tx;
     bf16 h = __float2bfloat16_rn(0.f), l = h;
-    if (r < R && c < C) {
-      const float xv = X[(size_t)r * ld + c];
+    if (r < J.R && c < J.C) {
+      const float xv = J.X[(size_t)r * J.ld + c];
       split_bf16(xv, h, l);
-      if (hi) {
-        hi[(size_t)r * C + c] = h;
-        lo[(size_t)r * C + c] = l;
+      if (J.hi) {
+        J.hi[(size_t)r * J.C + c] = h;
+        J.lo[(size_t)r * J.C + c] = l;
       }
-      if (lo2) lo2[(size_t)r * C + c] = __float2bfloat16_rn((xv - __bfloat162float(h)) - __bfloat162float(l));
+      if (J.lo2) J.lo2[(size_t)r * J.C + c] = __float2bfloat16_rn((xv - __bfloat162float(h)) - __bfloat162float(l));
     }
     s_hi[ty + i * 8][tx] = h;
     s_lo[ty + i * 8][tx] = l;
   }
-  if (!thi) return;
+  if (!J.thi) return;
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + i * 8, r = r0 + tx;
-    if (r < R && c < C) {
-      thi[(size_t)c * ldt + tcol0 + r] = s_hi[tx][ty + i * 8];
-      tlo[(size_t)c * ldt + tcol0 + r] = s_lo[tx][ty + i * 8];
+    if (r < J.R && c < J.C) {
+      J.thi[(size_t)c * J.ldt + J.tcol0 + r] = s_hi[tx][ty + i * 8];
+      J.tlo[(size_t)c * J.ldt + J.tcol0 + r] = s_lo[tx][ty + i * 8];
     }
   }
 }
 
-// bf16 hi/lo [R, C] -> transposed hi/lo [C, ldt], column = tcol0 + r
+// bf16 hi/lo [R, C] -> transposed hi/lo [C, ldt], column = tcol0 + r + (r >= split_row ? shift : 0): the query rows and
+// the document rows of a step land in their own 64-aligned column ranges with one launch
 __global__ void __launch_bounds__(256) transpose_pair_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo,
                                                              int R, int C, bf16* __restrict__ thi,
-                                                             bf16* __restrict__ tlo, int ldt, int tcol0) {
+                                                             bf16* __restrict__ tlo, int ldt, int tcol0, int split_row,
+                                                             int shift) {
   __shared__ bf16 s[2][32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -266,8 +284,9 @@ __global__ void __launch_bounds__(256) transpose_pair_kernel(const bf16* __restr
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + i * 8, r = r0 + tx;
     if (r < R && c < C) {
-      thi[(size_t)c * ldt + tcol0 + r] = s[0][tx][ty + i * 8];
-      tlo[(size_t)c * ldt + tcol0 + r] = s[1][tx][ty + i * 8];
+      const int col = tcol0 + r + (r >= split_row ? shift : 0);
+      thi[(size_t)c * ldt + col] = s[0][tx][ty + i * 8];
+      tlo[(size_t)c * ldt + col] = s[1][tx][ty + i * 8];
     }
   }
 }
@@ -369,13 +388,16 @@ int launch_gemm(const GemmDesc* d, int ngroups, int n_pairs, int splits, float* 
   gemm_tn_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(p);
   TT_LAUNCH_CHECK();
   if (use_partial) {
+    size_t n[2] = {0, 0};
     for (int i = 0; i < ngroups; ++i) {
-      const size_t n = (size_t)d[i].M * d[i].N;
+      n[i] = (size_t)d[i].M * d[i].N;
       TT_REQUIRE(d[i].ldc == 0 || d[i].ldc == d[i].N, "gemm: split-K output must be dense");
-      splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(p.g[i].partial, splits, n, d[i].C,
-                                                                           accumulate);
-      TT_LAUNCH_CHECK();
     }
+    const size_t nmax = n[0] > n[1] ? n[0] : n[1];
+    splitk_reduce_kernel<<<dim3((unsigned)((nmax / 4 + 255) / 256), ngroups), 256, 0, st>>>(
+        p.g[0].partial, d[0].C, n[0], ngroups > 1 ? p.g[1].partial : nullptr, ngroups > 1 ? d[1].C : nullptr, n[1],
+        splits, accumulate);
+    TT_LAUNCH_CHECK();
   } else {
     TT_REQUIRE(!accumulate, "gemm: accumulate needs the split-K path");  // checked before the launch in practice
   }
@@ -390,18 +412,29 @@ int choose_splits(int tiles, int K) {
   return max(s, 2);  // weight-gradient GEMMs always take the split-K path (it also implements `accumulate`)
 }
 
-int split_transpose(const float* X, int R, int C, long long ld, bf16* hi, bf16* lo, bf16* thi, bf16* tlo, int ldt,
-                    int tcol0, cudaStream_t st, bf16* lo2 = nullptr) {
-  dim3 grid((C + 31) / 32, (R + 31) / 32);
-  split_transpose_kernel<<<grid, 256, 0, st>>>(X, R, C, ld, hi, lo, lo2, thi, tlo, ldt, tcol0);
+int split_jobs(const SplitJob* jobs, int n, cudaStream_t st) {
+  SplitJobs J{};
+  int rmax = 0, cmax = 0;
+  for (int i = 0; i < n; ++i) {
+    J.j[i] = jobs[i];
+    rmax = max(rmax, jobs[i].R);
+    cmax = max(cmax, jobs[i].C);
+  }
+  split_transpose_kernel<<<dim3((cmax + 31) / 32, (rmax + 31) / 32, n), 256, 0, st>>>(J);
   TT_LAUNCH_CHECK();
   return 0;
 }
 
+int split_transpose(const float* X, int R, int C, long long ld, bf16* hi, bf16* lo, bf16* thi, bf16* tlo, int ldt,
+                    int tcol0, cudaStream_t st, bf16* lo2 = nullptr) {
+  SplitJob j{X, R, C, ld, hi, lo, lo2, thi, tlo, ldt, tcol0};
+  return split_jobs(&j, 1, st);
+}
+
 int transpose_pair(const bf16* hi, const bf16* lo, int R, int C, bf16* thi, bf16* tlo, int ldt, int tcol0,
-                   cudaStream_t st) {
+                   int split_row, int shift, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (R + 31) / 32);
-  transpose_pair_kernel<<<grid, 256, 0, st>>>(hi, lo, R, C, thi, tlo, ldt, tcol0);
+  transpose_pair_kernel<<<grid, 256, 0, st>>>(hi, lo, R, C, thi, tlo, ldt, tcol0, split_row, shift);
   TT_LAUNCH_CHECK();
   return 0;
 }
@@ -533,7 +566,7 @@ struct StepWs {
   bf16 *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;    // [3B,P], [P,ldt]
   bf16 *w1_hi[2], *w1_lo[2], *w1_lo2[2], *w1t_hi[2], *w1t_lo[2];  // per tower: [P,H], [H,P]
   bf16 *w2_hi[2], *w2_lo[2], *w2t_hi[2], *w2t_lo[2];  // per tower: [P,P], [P,P]
-  float *dz1, *partial, *colsum;
+  float *dz1, *partial, *colsum, *loss_scratch;
 };
 
 size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out) {
@@ -560,6 +593,7 @@ size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out)
   w.dz1 = ws_take<float>(p, R * P);
   w.partial = ws_take<float>(p, (size_t)2 * 32 * P * max(P, H));
   w.colsum = ws_take<float>(p, (size_t)2 * kColsumSlices * P);
+  w.loss_scratch = ws_take<float>(p, (size_t)(B + 3) / 4 + 8);
   (void)train_table;
   if (out) *out = w;
   return (size_t)(p - base) + 256;
@@ -589,16 +623,16 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
   PoolParams pp = s.pool;
   pp.x_hi = w.x_hi; pp.x_lo = w.x_lo; pp.x_lo2 = (np == 3) ? w.x_lo2 : nullptr; pp.xt_hi = nullptr; pp.xt_lo = nullptr;
   if ((rc = pool_fwd_launch(pp, s.table_dtype, H, st))) return rc;
-  for (int t = 0; t < 2; ++t)
-    if ((rc = transpose_pair(w.x_hi + (size_t)row0[t] * H, w.x_lo + (size_t)row0[t] * H, rows[t], H, w.xt_hi, w.xt_lo,
-                             w.ldt, tcol[t], st)))
-      return rc;
-  // 2. weights of both towers -> bf16 splits (+ transposes for the backward contractions)
-  for (int t = 0; t < 2; ++t) {
-    if ((rc = split_transpose(W1[t], P, H, H, w.w1_hi[t], w.w1_lo[t], s.dxhat ? w.w1t_hi[t] : nullptr,
-                              s.dxhat ? w.w1t_lo[t] : nullptr, P, 0, st, w.w1_lo2[t])))
-      return rc;
-    if ((rc = split_transpose(W2[t], P, P, P, w.w2_hi[t], w.w2_lo[t], w.w2t_hi[t], w.w2t_lo[t], P, 0, st))) return rc;
+  if ((rc = transpose_pair(w.x_hi, w.x_lo, 3 * B, H, w.xt_hi, w.xt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
+  // 2. weights of both towers -> bf16 terms (+ transposes for the backward contractions), one launch
+  {
+    SplitJob jobs[4];
+    for (int t = 0; t < 2; ++t) {
+      jobs[2 * t] = SplitJob{W1[t], P, H, H, w.w1_hi[t], w.w1_lo[t], np == 3 ? w.w1_lo2[t] : nullptr,
+                             s.dxhat ? w.w1t_hi[t] : nullptr, s.dxhat ? w.w1t_lo[t] : nullptr, P, 0};
+      jobs[2 * t + 1] = SplitJob{W2[t], P, P, P, w.w2_hi[t], w.w2_lo[t], nullptr, w.w2t_hi[t], w.w2t_lo[t], P, 0};
+    }
+    if ((rc = split_jobs(jobs, 4, st))) return rc;
   }
   // 3. h = relu(x W1^T + b1)  (fp32 + split + transposed split)
   GemmDesc g[2];
@@ -626,16 +660,12 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
   const float* yq = s.y;
   const float* yp = s.y + (size_t)B * P;
   const float* yn = s.y + (size_t)2 * B * P;
-  if ((rc = triplet_loss_fwd(yq, yp, yn, B, P, s.margin, s.inv_batch, s.stats, s.loss, st))) return rc;
   LossSplitOut so{};
   so.dy_hi = w.dy_hi; so.dy_lo = w.dy_lo;
-  if ((rc = triplet_loss_bwd(yq, yp, yn, s.stats, nullptr, s.grad_scale, B, P, s.inv_batch, s.dy, s.dy + (size_t)B * P,
-                             s.dy + (size_t)2 * B * P, &so, st)))
+  if ((rc = triplet_loss_fused(yq, yp, yn, B, P, s.margin, s.inv_batch, s.grad_scale, s.stats, s.loss, s.dy,
+                               s.dy + (size_t)B * P, s.dy + (size_t)2 * B * P, &so, w.loss_scratch, st)))
     return rc;
-  for (int t = 0; t < 2; ++t)
-    if ((rc = transpose_pair(w.dy_hi + (size_t)row0[t] * P, w.dy_lo + (size_t)row0[t] * P, rows[t], P, w.dyt_hi,
-                             w.dyt_lo, w.ldt, tcol[t], st)))
-      return rc;
+  if ((rc = transpose_pair(w.dy_hi, w.dy_lo, 3 * B, P, w.dyt_hi, w.dyt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
   // 6. db2, dW2 = dY^T h   (split-K over the batch rows)
   if ((rc = colsum2(s.dy, rows[0], db2[0], s.dy + (size_t)row0[1] * P, rows[1], db2[1], P, P, 0, w.colsum, st))) return rc;
   for (int t = 0; t < 2; ++t) {

@@ -98,7 +98,101 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// fused forward + backward (one warp per triplet, rows re-read from L1 for the gradient)
+__global__ void __launch_bounds__(128)
+    triplet_fused_kernel(const float* __restrict__ q, const float* __restrict__ p, const float* __restrict__ n, int B,
+                         int P, float margin, float inv_batch, float grad_scale, float* __restrict__ stats,
+                         float* __restrict__ loss, float* __restrict__ dq, float* __restrict__ dp,
+                         float* __restrict__ dn, LossSplitOut sp, float* __restrict__ scratch) {
+  __shared__ float s_h[4];
+  __shared__ int s_last;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + w;
+  float hinge = 0.f;
+  if (i < B) {
+    const size_t o = (size_t)i * P;
+    float qq = 0.f, pp = 0.f, nn = 0.f, qp = 0.f, qn = 0.f;
+    for (int c = lane; c < P; c += 32) {
+      const float a = q[o + c], b = p[o + c], d = n[o + c];
+      qq = fmaf(a, a, qq);
+      pp = fmaf(b, b, pp);
+      nn = fmaf(d, d, nn);
+      qp = fmaf(a, b, qp);
+      qn = fmaf(a, d, qn);
+    }
+    qq = warp_sum(qq); pp = warp_sum(pp); nn = warp_sum(nn); qp = warp_sum(qp); qn = warp_sum(qn);
+    const float nq = sqrtf(qq), np_ = sqrtf(pp), nn_ = sqrtf(nn);
+    const float cq = fmaxf(nq, kCosEps), cp = fmaxf(np_, kCosEps), cn = fmaxf(nn_, kCosEps);
+    const float cos_p = qp / (cq * cp), cos_n = qn / (cq * cn);
+    hinge = fmaxf((1.f - cos_p) - (1.f - cos_n) + margin, 0.f);
+    if (lane == 0) {
+      float* s = stats + (size_t)i * 8;
+      s[0] = cos_p; s[1] = cos_n; s[2] = hinge; s[3] = nq; s[4] = np_; s[5] = nn_; s[6] = qp; s[7] = qn;
+    }
+    const float gh = (hinge > 0.f) ? grad_scale * inv_batch : 0.f;
+    const float a_qp = -gh / (cq * cp), a_qn = gh / (cq * cn);
+    const float kq = (nq > kCosEps) ? (-gh * cos_p + gh * cos_n) / (cq * nq) : 0.f;
+    const float kp = (np_ > kCosEps) ? (-gh * cos_p) / (cp * np_) : 0.f;
+    const float kn = (nn_ > kCosEps) ? (gh * cos_n) / (cn * nn_) : 0.f;
+    for (int c = lane; c < P; c += 32) {
+      const float a = q[o + c], b = p[o + c], d = n[o + c];
+      const float gv[3] = {a_qp * b + a_qn * d - kq * a, a_qp * a - kp * b, a_qn * a - kn * d};
+      dq[o + c] = gv[0];
+      dp[o + c] = gv[1];
+      dn[o + c] = gv[2];
+      if (sp.dy_hi) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          __nv_bfloat16 hi, lo;
+          split_bf16(gv[t], hi, lo);
+          const size_t row = (size_t)t * B + i;
+          sp.dy_hi[row * P + c] = hi;
+          sp.dy_lo[row * P + c] = lo;
+        }
+      }
+    }
+  }
+  if (lane == 0) s_h[w] = hinge;
+  __syncthreads();
+  const int nblk = gridDim.x;
+  unsigned* counter = reinterpret_cast<unsigned*>(scratch + nblk + 1);
+  if (threadIdx.x == 0) {
+    scratch[blockIdx.x] = (s_h[0] + s_h[1]) + (s_h[2] + s_h[3]);
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == (unsigned)nblk - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last block: fixed-order sum of the per-block partials (independent of which block arrived last)
+  __shared__ float s_red[128];
+  float v = 0.f;
+  for (int b = threadIdx.x; b < nblk; b += 128) v += __ldcg(scratch + b);
+  s_red[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (threadIdx.x < off) s_red[threadIdx.x] += s_red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *loss = s_red[0] * inv_batch;
+    *counter = 0u;  // ready for the next launch / graph replay
+  }
+}
+
 }  // namespace
+
+int triplet_loss_fused(const float* q, const float* p, const float* n, int B, int P, float margin, float inv_batch,
+                       float grad_scale, float* stats, float* loss, float* dq, float* dp, float* dn,
+                       const LossSplitOut* split, float* scratch, cudaStream_t st) {
+  TT_REQUIRE(B >= 1, "triplet loss: empty batch");
+  LossSplitOut sp{};
+  if (split) sp = *split;
+  triplet_fused_kernel<<<(B + 3) / 4, 128, 0, st>>>(q, p, n, B, P, margin, inv_batch, grad_scale, stats, loss, dq, dp, dn,
+                                                    sp, scratch);
+  TT_LAUNCH_CHECK();
+  return 0;
+}
 
 int triplet_loss_fwd(const float* q, const float* p, const float* n, int B, int P, float margin, float inv_batch,
                      float* stats, float* loss, cudaStream_t st) {

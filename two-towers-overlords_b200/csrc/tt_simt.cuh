@@ -44,6 +44,12 @@ struct LossSplitOut {  // optional operands for the tensor-core backward: dY as 
 };
 int triplet_loss_fwd(const float* q, const float* p, const float* n, int B, int P, float margin, float inv_batch,
                      float* stats, float* loss, cudaStream_t st);
+// forward + backward in one launch (the fused step): per-block hinge sums go to scratch[0 .. ceil(B/4)), the last block
+// to finish adds them in index order (deterministic) and writes the loss; scratch[ceil(B/4) + 1] is the arrival counter,
+// which must be zero before the first call (it is reset by the kernel, so graph replays need no memset)
+int triplet_loss_fused(const float* q, const float* p, const float* n, int B, int P, float margin, float inv_batch,
+                       float grad_scale, float* stats, float* loss, float* dq, float* dp, float* dn,
+                       const LossSplitOut* split, float* scratch, cudaStream_t st);
 int triplet_loss_bwd(const float* q, const float* p, const float* n, const float* stats, const float* dloss,
                      float grad_scale, int B, int P, float inv_batch, float* dq, float* dp, float* dn,
                      const LossSplitOut* split, cudaStream_t st);

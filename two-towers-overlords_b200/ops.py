@@ -204,7 +204,7 @@ class TripletStep:
         self.prec = _prec(precision)
         self.train_table = bool(train_table)
         self.ws_bytes = self.lib.tt_step_ws_bytes(B, Lq, Ld, H, P, vocab, self.prec, int(self.train_table))
-        self.ws = N.workspace(self.ws_bytes, device)
+        self.ws = N.workspace(self.ws_bytes, device).zero_()  # tt_triplet_step wants a zero-filled workspace once
         self.loss = torch.zeros((), dtype=torch.float32, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.args = N.StepArgs()
