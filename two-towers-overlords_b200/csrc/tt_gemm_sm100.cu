@@ -11,6 +11,8 @@
 //     (tcgen05.ld 32 lanes x 16 columns per warp quarter), STAGES-deep mbarrier ring between producer and issuer;
 //   * up to two problem groups per launch (query tower | document tower) and split-K over blockIdx.z for the
 //     weight-gradient contractions (K = batch rows), reduced afterwards in a fixed order (deterministic).
+#include <stdlib.h>
+
 #include "tt_ptx.cuh"
 #include "tt_simt.cuh"
 #include "tt_sm100.cuh"
@@ -24,10 +26,10 @@ using bf16 = __nv_bfloat16;
 using namespace ptx;
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 3;  // 3 x 32 KB: two CTAs per SM, so one CTA's epilogue overlaps the other's main loop
+constexpr int kMaxStages = 6;
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t gemm_smem(int stages) { return (size_t)stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct alignas(64) GemmGroup {
   CUtensorMap a[3], b[3];  // bf16 terms of each operand: hi, lo (= fp32 - hi), lo2 (= fp32 - hi - lo)
@@ -44,7 +46,8 @@ struct alignas(64) GemmGroup {
 
 struct alignas(64) GemmParams {
   GemmGroup g[2];
-  int ngroups, splits, n_pairs, pad;
+  int ngroups, splits, n_pairs;
+  int stages;  // ring of 32 KB (A tile, B tile) slots; a k-block occupies `terms` consecutive slots
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_constant__ GemmParams p) {
@@ -57,29 +60,30 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
+  const int NS = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * kStageBytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tmem_full = empty + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int kb_total = (g.K + BK - 1) / BK;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
   const int kb0 = split * kb_per;
-  const int kb1 = min(kb0 + kb_per, kb_total);
-  const int n_iter = (kb1 - kb0) * p.n_pairs;  // >= 1: the host never creates an empty split
+  const int n_kb = min(kb0 + kb_per, kb_total) - kb0;  // >= 1: the host never creates an empty split
+  // Each k-block brings every bf16 term of both operands exactly once: slot j of the block holds (A term j, B term j);
+  // the MMAs then combine terms across slots (hi*hi, hi*lo, lo*hi | lo*lo, hi*lo2, lo2*hi).
+  const int T = p.n_pairs == 1 ? 1 : (p.n_pairs == 3 ? 2 : 3);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
-    prefetch_tensormap(&g.a[0]);
-    prefetch_tensormap(&g.b[0]);
-    if (p.n_pairs > 1) {
-      prefetch_tensormap(&g.a[1]);
-      prefetch_tensormap(&g.b[1]);
+    for (int j = 0; j < T; ++j) {
+      prefetch_tensormap(&g.a[j]);
+      prefetch_tensormap(&g.b[j]);
     }
   }
   if (warp == 1) {
@@ -93,34 +97,39 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer --------------------------------------------------------------------
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        const int pair = it % p.n_pairs, kb = kb0 + it / p.n_pairs;
-        // product terms in order: hi*hi, hi*lo, lo*hi | lo*lo, hi*lo2, lo2*hi  (1, 3 or 6 of them)
-        const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
-        const CUtensorMap* ma = &g.a[ai];
-        const CUtensorMap* mb = &g.b[bi];
-        mbar_arrive_expect_tx(&full[s], kStageBytes);
-        tma_load_2d(smem + s * kStageBytes, ma, &full[s], kb * BK, m0);
-        tma_load_2d(smem + s * kStageBytes + kABytes, mb, &full[s], kb * BK, n0);
+      int it = 0;
+      for (int kbi = 0; kbi < n_kb; ++kbi) {
+        for (int j = 0; j < T; ++j, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          tma_load_2d(smem + s * kStageBytes, &g.a[j], &full[s], (kb0 + kbi) * BK, m0);
+          tma_load_2d(smem + s * kStageBytes + kABytes, &g.b[j], &full[s], (kb0 + kbi) * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer ------------------------------------------------------------------------
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-        mbar_wait(&full[s], ph);
+      const uint32_t ring = smem_u32(smem);
+      int it = 0;
+      for (int kbi = 0; kbi < n_kb; ++kbi, it += T) {
+        uint32_t slot_addr[3];
+        for (int j = 0; j < T; ++j) {
+          const int s = (it + j) % NS;
+          mbar_wait(&full[s], (uint32_t)((it + j) / NS) & 1u);
+          slot_addr[j] = ring + (uint32_t)s * kStageBytes;
+        }
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-        const uint64_t da = make_smem_desc_sw128(a_addr), db = make_smem_desc_sw128(a_addr + kABytes);
+        for (int pair = 0; pair < p.n_pairs; ++pair) {
+          const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
+          const uint64_t da = make_smem_desc_sw128(slot_addr[ai]), db = make_smem_desc_sw128(slot_addr[bi] + kABytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
-          mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-        mma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
+            mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kbi | pair | k) != 0);
+        }
+        for (int j = 0; j < T; ++j) mma_commit(&empty[(it + j) % NS]);  // frees the slots once these MMAs have read them
       }
       mma_commit(tmem_full);
     }
@@ -337,9 +346,21 @@ int fill_group(GemmGroup& g, const GemmDesc& d, int n_pairs) {
 int ensure_gemm_attr() {
   static bool done = false;
   if (done) return 0;
-  TT_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+  TT_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem(kMaxStages)));
   done = true;
   return 0;
+}
+
+// ring depth: 3 slots (98 KB) keep two CTAs per SM, so one CTA's epilogue overlaps the other's main loop;
+// TT_GEMM_STAGES overrides (tuning hook)
+int gemm_stages(int n_pairs) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("TT_GEMM_STAGES");
+    env = e ? atoi(e) : 0;
+  }
+  if (env >= 3 && env <= kMaxStages) return env;
+  return n_pairs == 6 ? 3 : 3;
 }
 
 // Launches 1 or 2 problem groups.  partial != nullptr: every group is a split-K contraction whose raw partial sums
@@ -384,8 +405,9 @@ int launch_gemm(const GemmDesc* d, int ngroups, int n_pairs, int splits, float* 
       off += (size_t)splits * d[i].M * d[i].N;
     }
   }
+  p.stages = gemm_stages(n_pairs);
   dim3 grid(tiles_n, tiles_m, ngroups * splits);
-  gemm_tn_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(p);
+  gemm_tn_kernel<<<grid, kGemmThreads, gemm_smem(p.stages), st>>>(p);
   TT_LAUNCH_CHECK();
   if (use_partial) {
     size_t n[2] = {0, 0};

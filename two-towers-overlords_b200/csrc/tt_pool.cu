@@ -5,6 +5,8 @@
 // A warp reads one row per step as fully coalesced 16 B (fp32) / 8 B (bf16) per-lane vectors,
 // UNROLL rows in flight per warp, 4 warps per sequence, fp32 accumulation in registers, cross-warp
 // reduction staged in shared memory, warp-shuffle reduction for the norm.
+#include <stdlib.h>
+
 #include "tt_pool.cuh"
 
 namespace tt {
@@ -46,7 +48,7 @@ struct RowVec<__nv_bfloat16> {
   }
 };
 
-template <typename TE, int NV, int UNROLL>
+template <typename TE, int NV, int UNROLL, bool PIPE>
 __global__ void __launch_bounds__(kPoolThreads) pool_fwd_kernel(const PoolParams p) {
   constexpr int H = NV * 128;
   __shared__ unsigned s_row[kMaxL];
@@ -136,24 +138,34 @@ __global__ void __launch_bounds__(kPoolThreads) pool_fwd_kernel(const PoolParams
 #pragma unroll
       for (int j = 0; j < NV; ++j) dst[u][j] = RV::load(rows[u], j * 32 + lane);
   };
-  if (warp < n_valid) issue(warp, v, wt);
-  for (int e0 = warp; e0 < n_valid; e0 += kPoolWarps * UNROLL) {
-    typename RV::V vn[UNROLL][NV];
-    float wn[UNROLL];
-    const int e1 = e0 + kPoolWarps * UNROLL;
-    const bool more = e1 < n_valid;
-    if (more) issue(e1, vn, wn);
+  if (PIPE) {
+    if (warp < n_valid) issue(warp, v, wt);
+    for (int e0 = warp; e0 < n_valid; e0 += kPoolWarps * UNROLL) {
+      typename RV::V vn[UNROLL][NV];
+      float wn[UNROLL];
+      const int e1 = e0 + kPoolWarps * UNROLL;
+      const bool more = e1 < n_valid;
+      if (more) issue(e1, vn, wn);
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+      for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-      for (int j = 0; j < NV; ++j) RV::fma(wt[u], v[u][j], acc + j * 4);
-    if (more) {
+        for (int j = 0; j < NV; ++j) RV::fma(wt[u], v[u][j], acc + j * 4);
+      if (more) {
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        wt[u] = wn[u];
+        for (int u = 0; u < UNROLL; ++u) {
+          wt[u] = wn[u];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) v[u][j] = vn[u][j];
+          for (int j = 0; j < NV; ++j) v[u][j] = vn[u][j];
+        }
       }
+    }
+  } else {  // one batch of UNROLL rows in flight per warp; latency is hidden by the other resident warps
+    for (int e0 = warp; e0 < n_valid; e0 += kPoolWarps * UNROLL) {
+      issue(e0, v, wt);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) RV::fma(wt[u], v[u][j], acc + j * 4);
     }
   }
 
@@ -225,10 +237,24 @@ __global__ void __launch_bounds__(kPoolThreads) pool_fwd_kernel(const PoolParams
   }
 }
 
+int pool_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TT_POOL_VARIANT");  // tuning hook: 0 = register-pipelined x4, 1 = x4 (default: 54 regs, 36 warps/SM), 2 = x8, 3 = pipelined x2
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 template <typename TE, int NV>
 int launch_pool(const PoolParams& p, int total, cudaStream_t st) {
   constexpr int UNROLL = sizeof(TE) == 4 ? 4 : 8;
-  pool_fwd_kernel<TE, NV, UNROLL><<<total, kPoolThreads, 0, st>>>(p);
+  switch (pool_variant()) {
+    case 1: pool_fwd_kernel<TE, NV, UNROLL, false><<<total, kPoolThreads, 0, st>>>(p); break;
+    case 2: pool_fwd_kernel<TE, NV, UNROLL * 2, false><<<total, kPoolThreads, 0, st>>>(p); break;
+    case 3: pool_fwd_kernel<TE, NV, UNROLL / 2, true><<<total, kPoolThreads, 0, st>>>(p); break;
+    default: pool_fwd_kernel<TE, NV, UNROLL, true><<<total, kPoolThreads, 0, st>>>(p); break;
+  }
   TT_LAUNCH_CHECK();
   return 0;
 }
