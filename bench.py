@@ -150,7 +150,7 @@ def run_reference(args):
     value, info = cpu_train_throughput(0, steps=args.steps, warmup=max(1, args.warmup), batch=B)
     sample = (f"{args.steps} fp32 steps of {B} triplets (of the {B_PER_GPU}-triplet batch), oracle port of "
               f"backend/training.py:36-53 with the embedding-only backbone, torch CPU, {info['cores']} threads")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -337,7 +337,7 @@ def run_b200(args):
         scan = run_scan(dev, world, rank, args.scan_docs, args.scan_queries, HIDDEN, args.scan_passes)
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else f"f32 ({args.precision} tensor-core projection)",
@@ -456,6 +456,24 @@ def run_scan(dev, world, rank, n_docs, n_queries, P, passes, precision="bf16"):
     }
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Native libraries (NCCL's version banner) write to fd 1; keep stdout to the ONE JSON line by pointing fd 1 at
+    stderr for the whole run and printing the result on the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -474,6 +492,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -97,15 +97,18 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer --------------------------------------------------------------------
-      int it = 0;
+      int s = 0;  // ring slot and its phase, advanced incrementally (no integer division in the hot loops)
+      uint32_t ph = 0;
       for (int kbi = 0; kbi < n_kb; ++kbi) {
-        for (int j = 0; j < T; ++j, ++it) {
-          const int s = it % NS;
-          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+        for (int j = 0; j < T; ++j) {
           mbar_wait(&empty[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full[s], kStageBytes);
           tma_load_2d(smem + s * kStageBytes, &g.a[j], &full[s], (kb0 + kbi) * BK, m0);
           tma_load_2d(smem + s * kStageBytes + kABytes, &g.b[j], &full[s], (kb0 + kbi) * BK, n0);
+          if (++s == NS) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
@@ -113,13 +116,19 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
     if (lane == 0) {  // ---- MMA issuer ------------------------------------------------------------------------
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       const uint32_t ring = smem_u32(smem);
-      int it = 0;
-      for (int kbi = 0; kbi < n_kb; ++kbi, it += T) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kbi = 0; kbi < n_kb; ++kbi) {
         uint32_t slot_addr[3];
+        int slot_id[3];
         for (int j = 0; j < T; ++j) {
-          const int s = (it + j) % NS;
-          mbar_wait(&full[s], (uint32_t)((it + j) / NS) & 1u);
+          mbar_wait(&full[s], ph);
+          slot_id[j] = s;
           slot_addr[j] = ring + (uint32_t)s * kStageBytes;
+          if (++s == NS) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
         tc_fence_after();
         for (int pair = 0; pair < p.n_pairs; ++pair) {
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
           for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
             mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kbi | pair | k) != 0);
         }
-        for (int j = 0; j < T; ++j) mma_commit(&empty[(it + j) % NS]);  // frees the slots once these MMAs have read them
+        for (int j = 0; j < T; ++j) mma_commit(&empty[slot_id[j]]);  // frees the slots once these MMAs have read them
       }
       mma_commit(tmem_full);
     }

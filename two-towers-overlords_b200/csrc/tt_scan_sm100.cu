@@ -31,16 +31,18 @@ constexpr int TQ = 128, TD = 128, BK = 64;
 constexpr int kScanThreads = 192;
 constexpr uint32_t kTileBytes = TD * BK * 2;  // 16 KB: one 128-row x 64-k bf16 tile (queries or documents)
 constexpr int kMaxKC = 48;
-constexpr int kSlack = 32;  // append room beyond KC between two compactions (>= 16: one tcgen05.ld chunk)
+constexpr int kSlack = 64;  // append room beyond KC: a compaction runs when fewer than 32 (one TMEM chunk) slots remain
 constexpr int kMaxSplits = 148;
+constexpr int kTmemCols = 512;  // [0,256): two 128-column score accumulators, [256, 256 + P/2): the query tile
 constexpr size_t kSmemLimit = 227 * 1024;
 // |bf16(q).bf16(d) - q.d| <= |q - q~||d| + |q~||d - d~| <= 2^-9 + 2^-9 (1 + 2^-9) for rows of norm <= 1, plus the
 // tensor-core accumulation error (< 1e-6): a rigorous, deliberately loose bound
 constexpr float kScanEps = 4e-3f;
 
 struct alignas(64) ScanParams {
-  CUtensorMap q_map, d_map;
-  int Q, KB, KC, stages;
+  CUtensorMap d_map;
+  const bf16* Qb;  // [Q, P] normalised queries, bf16
+  int Q, P, KB, KC, stages, stagger;
   long long N, docs_per_split;
   float* cand_s;   // [S, Q, KC] approximate scores (diagnostic / tie information)
   int* cand_i;     // [S, Q, KC] local document index, -1 = empty
@@ -55,11 +57,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
   const long long d_end = min(d_beg + p.docs_per_split, p.N);
   const int n_tiles = d_end > d_beg ? (int)((d_end - d_beg + TD - 1) / TD) : 0;
   const int KB = p.KB, NS = p.stages, KC = p.KC;
+  // CTAs of one wave share a document range through L2; starting each a few tiles apart keeps them inside an
+  // L2-sized window (so HBM still sees every tile once per wave) without all SMs hitting the same lines at once
+  const int stagger = n_tiles > 0 ? (int)((blockIdx.x % 148u) * (unsigned)p.stagger) % n_tiles : 0;
 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* q_tile = smem;                               // KB x 16 KB
-  uint8_t* d_ring = smem + (size_t)KB * kTileBytes;     // NS x 16 KB
+  uint8_t* d_ring = smem;                               // NS x 16 KB
   float* list_s = reinterpret_cast<float*>(d_ring + (size_t)NS * kTileBytes);  // [KC + kSlack][128]
   int* list_i = reinterpret_cast<int*>(list_s + (KC + kSlack) * TQ);           // [KC + kSlack][128]
   uint64_t* full = reinterpret_cast<uint64_t*>(list_i + (KC + kSlack) * TQ);
@@ -74,17 +78,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(q_full, 1);
+    mbar_init(q_full, 4);  // one arrive per epilogue warp once its 32 query rows sit in TMEM
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
     }
     fence_barrier_init();
-    prefetch_tensormap(&p.q_map);
     prefetch_tensormap(&p.d_map);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * TD);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -94,17 +97,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
 
   if (warp == 0) {
     if (lane == 0 && n_tiles > 0) {  // ---- TMA producer ---------------------------------------------------------
-      mbar_arrive_expect_tx(q_full, (uint32_t)KB * kTileBytes);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(q_tile + (size_t)kb * kTileBytes, &p.q_map, q_full, kb * BK, q0);
-      int it = 0;
+      int s = 0;            // ring slot and its phase, advanced incrementally (no integer division in the hot loops)
+      uint32_t ph = 0;
+      int tt_ = stagger;
       for (int t = 0; t < n_tiles; ++t) {
-        const int d0 = (int)(d_beg + (long long)t * TD);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % NS;
-          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+        const int d0 = (int)(d_beg + (long long)tt_ * TD);
+        if (++tt_ == n_tiles) tt_ = 0;
+        for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full[s], kTileBytes);
           tma_load_2d(d_ring + (size_t)s * kTileBytes, &p.d_map, &full[s], kb * BK, d0);
+          if (++s == NS) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
@@ -113,23 +119,27 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       constexpr uint32_t idesc = make_idesc_bf16(TQ, TD);
       mbar_wait(q_full, 0);
       tc_fence_after();
-      const uint32_t q_addr = smem_u32(q_tile), r_addr = smem_u32(d_ring);
-      int it = 0;
+      const uint32_t r_addr = smem_u32(d_ring);
+      const uint32_t a_tmem = tmem_base + (uint32_t)(2 * TD);  // query tile: 32 columns per 64-wide k-block
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
         mbar_wait(&tmem_empty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % NS;
-          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+        for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint64_t da = make_smem_desc_sw128(q_addr + (uint32_t)kb * kTileBytes);
           const uint64_t db = make_smem_desc_sw128(r_addr + (uint32_t)s * kTileBytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            mma_bf16(tmem_base + (uint32_t)(buf * TD), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            mma_bf16_ts(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
+                        (kb | k) != 0);
           mma_commit(&empty[s]);
+          if (++s == NS) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
         mma_commit(&tmem_full[buf]);
       }
@@ -147,6 +157,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
     int* li = list_i + t_row;
     float thr = q_ok ? -INFINITY : INFINITY;  // rows past Q never append
     int cnt = 0;
+    {  // A operand: this thread's query row -> its TMEM lane, two bf16 per 32-bit column, zero beyond P / past Q
+      const uint4* qrow = reinterpret_cast<const uint4*>(p.Qb + (size_t)(q0 + t_row) * p.P);
+      const int n_vec = p.P / 8;  // uint4 = 8 bf16
+      for (int c = 0; c < KB * 2; ++c) {  // 16 columns = 32 bf16 = 4 uint4 per store
+        uint32_t r[16];
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int vi = c * 4 + v4;
+          uint4 x = make_uint4(0u, 0u, 0u, 0u);
+          if (q_ok && vi < n_vec) x = __ldg(qrow + vi);
+          r[v4 * 4 + 0] = x.x; r[v4 * 4 + 1] = x.y; r[v4 * 4 + 2] = x.z; r[v4 * 4 + 3] = x.w;
+        }
+        tmem_st16(tmem_base + (uint32_t)(2 * TD) + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 16), r);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full);
+    }
     auto compact = [&]() {
       const int nmax = __reduce_max_sync(0xffffffffu, cnt);
       const int rounds = min(KC, nmax);
@@ -178,27 +207,43 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       const int buf = t & 1;
       mbar_wait(&tmem_full[buf], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
-      const int d0 = t * TD;  // local to the split
+      int tt_ = t + stagger;
+      if (tt_ >= n_tiles) tt_ -= n_tiles;
+      const int d0 = tt_ * TD;  // local to the split
       const int nd = (int)min((long long)TD, d_end - d_beg - d0);
-      for (int c = 0; c < TD / 16; ++c) {
-        float v[16];
-        tmem_ld16(tmem_base + (uint32_t)(buf * TD) + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 16), v);
-        float m = v[0];
+      // 4 chunks of 32 scores, double-buffered in registers: the TMEM load of chunk c+1 flies while chunk c is scanned
+      const uint32_t t_addr = tmem_base + (uint32_t)(buf * TD) + ((uint32_t)(qd * 32) << 16);
+      uint32_t ra[32], rb[32];
+      auto scan32 = [&](const uint32_t* r, int c) {
+        float m = __uint_as_float(r[0]);
 #pragma unroll
-        for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
         if (m > thr) {  // rare once the threshold has settled
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int dj = c * 16 + j;
-            if (v[j] > thr && dj < nd) {
-              ls[cnt * TQ] = v[j];
+          for (int j = 0; j < 32; ++j) {
+            const int dj = c * 32 + j;
+            const float vj = __uint_as_float(r[j]);
+            if (vj > thr && dj < nd) {
+              ls[cnt * TQ] = vj;
               li[cnt * TQ] = d0 + dj;
               ++cnt;
             }
           }
         }
-        if (__any_sync(0xffffffffu, cnt > CAP - 16)) compact();  // warp-uniform: no lane can overflow next chunk
-      }
+        if (__any_sync(0xffffffffu, cnt > CAP - 32)) compact();  // warp-uniform: no lane can overflow next chunk
+      };
+      tmem_ld32_async(t_addr, ra);
+      tmem_ld_wait32(ra);
+      tmem_ld32_async(t_addr + 32, rb);
+      scan32(ra, 0);
+      tmem_ld_wait32(rb);
+      tmem_ld32_async(t_addr + 64, ra);
+      scan32(rb, 1);
+      tmem_ld_wait32(ra);
+      tmem_ld32_async(t_addr + 96, rb);
+      scan32(ra, 2);
+      tmem_ld_wait32(rb);
+      scan32(rb, 3);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -217,7 +262,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * TD);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 __device__ __forceinline__ bool better(float s1, long long i1, float s2, long long i2) {
@@ -379,17 +424,22 @@ int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
   size_t fixed = 0;
   int stages = 0;
   for (;; kc -= 16) {
-    fixed = 1024 + 512 + (size_t)pl.KB * kTileBytes + (size_t)(kc + kSlack) * TQ * 8;
+    fixed = 1024 + 512 + (size_t)(kc + kSlack) * TQ * 8;
     stages = fixed < kSmemLimit ? (int)((kSmemLimit - fixed) / kTileBytes) : 0;
     if (stages >= 3 || kc - 16 < k + 6 || kc <= 16) break;
   }
   pl.KC = kc;
-  if (stages > 8) stages = 8;
+  if (stages > 12) stages = 12;
   pl.stages = stages;
   pl.smem = fixed + (size_t)stages * kTileBytes;
   pl.cap = Q < 8192 ? Q : 8192;
   *out = pl;
   return 0;
+}
+
+int scan_stagger() {
+  const char* e = getenv("TT_SCAN_STAGGER");  // tuning hook: tiles between the starting points of neighbouring CTAs
+  return e ? atoi(e) : 4;
 }
 
 float scan_eps() {
@@ -449,9 +499,10 @@ int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void
   }
   ScanParams sp{};
   int rc;
-  if ((rc = make_map_bf16_kmajor(&sp.q_map, Qb, Q, P, P, TQ))) return rc;
   if ((rc = make_map_bf16_kmajor(&sp.d_map, Db, (uint64_t)N, P, P, TD))) return rc;
-  sp.Q = Q; sp.KB = pl.KB; sp.KC = pl.KC; sp.stages = pl.stages;
+  sp.Qb = reinterpret_cast<const bf16*>(Qb);
+  sp.stagger = scan_stagger();
+  sp.Q = Q; sp.P = P; sp.KB = pl.KB; sp.KC = pl.KC; sp.stages = pl.stages;
   sp.N = N; sp.docs_per_split = pl.docs_per_split;
   sp.cand_s = w.cand_s; sp.cand_i = w.cand_i; sp.bound = w.bound;
   scan_candidates_kernel<<<dim3(pl.n_qtiles, pl.S), kScanThreads, pl.smem, st>>>(sp);
