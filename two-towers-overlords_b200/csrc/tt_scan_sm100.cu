@@ -49,22 +49,33 @@ struct alignas(64) ScanParams {
   float* bound;    // [S, Q] KC-th best approximate score of the split, -inf if fewer than KC documents
 };
 
+// PAIR = true: two CTAs (a cluster of 2 along the query tiles) drive one cta_group::2 MMA of 256 queries x 128 documents:
+// each CTA holds its own 128 queries in TMEM and streams only 64 of the 128 documents of a tile, so the L2 and
+// shared-memory traffic per flop is half of the single-CTA kernel's.  The leader (cluster rank 0) issues the MMAs and
+// multicast commits; data-ready barriers live in the leader, slot-free / accumulator-ready barriers in both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const __grid_constant__ ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TQ, split = blockIdx.y;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr uint32_t kSlotBytes = PAIR ? kTileBytes / 2 : kTileBytes;  // documents of a tile held by this CTA x 64 k
+  constexpr int kOwnDocs = PAIR ? TD / 2 : TD;
+  constexpr uint32_t kEpiArrivals = PAIR ? 8 : 4;  // epilogue warps that must report to the MMA issuer
   const long long d_beg = (long long)split * p.docs_per_split;
   const long long d_end = min(d_beg + p.docs_per_split, p.N);
   const int n_tiles = d_end > d_beg ? (int)((d_end - d_beg + TD - 1) / TD) : 0;
   const int KB = p.KB, NS = p.stages, KC = p.KC;
   // CTAs of one wave share a document range through L2; starting each a few tiles apart keeps them inside an
   // L2-sized window (so HBM still sees every tile once per wave) without all SMs hitting the same lines at once
-  const int stagger = n_tiles > 0 ? (int)((blockIdx.x % 148u) * (unsigned)p.stagger) % n_tiles : 0;
+  const int stagger =
+      n_tiles > 0 ? (int)(((blockIdx.x / (PAIR ? 2u : 1u)) % 148u) * (unsigned)p.stagger) % n_tiles : 0;
 
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* d_ring = smem;                               // NS x 16 KB
-  float* list_s = reinterpret_cast<float*>(d_ring + (size_t)NS * kTileBytes);  // [KC + kSlack][128]
+  uint8_t* d_ring = smem;                               // NS slots
+  float* list_s = reinterpret_cast<float*>(d_ring + (size_t)NS * kSlotBytes);  // [KC + kSlack][128]
   int* list_i = reinterpret_cast<int*>(list_s + (KC + kSlack) * TQ);           // [KC + kSlack][128]
   uint64_t* full = reinterpret_cast<uint64_t*>(list_i + (KC + kSlack) * TQ);
   uint64_t* empty = full + NS;
@@ -78,35 +89,45 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(q_full, 4);  // one arrive per epilogue warp once its 32 query rows sit in TMEM
+    mbar_init(q_full, kEpiArrivals);  // one arrive per epilogue warp once its 32 query rows sit in TMEM
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[b], kEpiArrivals);  // one arrive per epilogue warp
     }
     fence_barrier_init();
     prefetch_tensormap(&p.d_map);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0 && n_tiles > 0) {  // ---- TMA producer ---------------------------------------------------------
+    if (lane == 0 && n_tiles > 0) {  // ---- TMA producer (both CTAs of a pair) -------------------------------------
       int s = 0;            // ring slot and its phase, advanced incrementally (no integer division in the hot loops)
       uint32_t ph = 0;
       int tt_ = stagger;
       for (int t = 0; t < n_tiles; ++t) {
-        const int d0 = (int)(d_beg + (long long)tt_ * TD);
+        const int d0 = (int)(d_beg + (long long)tt_ * TD) + (int)rank * kOwnDocs;
         if (++tt_ == n_tiles) tt_ = 0;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], kTileBytes);
-          tma_load_2d(d_ring + (size_t)s * kTileBytes, &p.d_map, &full[s], kb * BK, d0);
+          if (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&full[s], kTileBytes);  // both halves complete on the leader's barrier
+            tma_load_2d_pair(d_ring + (size_t)s * kSlotBytes, &p.d_map, mapa_shared(smem_u32(&full[s]), 0), kb * BK, d0);
+          } else {
+            mbar_arrive_expect_tx(&full[s], kTileBytes);
+            tma_load_2d(d_ring + (size_t)s * kSlotBytes, &p.d_map, &full[s], kb * BK, d0);
+          }
           if (++s == NS) {
             s = 0;
             ph ^= 1u;
@@ -115,8 +136,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_tiles > 0) {  // ---- MMA issuer -------------------------------------------------------------
-      constexpr uint32_t idesc = make_idesc_bf16(TQ, TD);
+    if (lane == 0 && n_tiles > 0 && leader) {  // ---- MMA issuer (leader CTA only) --------------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TQ : TQ, TD);
       mbar_wait(q_full, 0);
       tc_fence_after();
       const uint32_t r_addr = smem_u32(d_ring);
@@ -125,23 +146,28 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
-        mbar_wait(&tmem_empty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue(s) drained this accumulator
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint64_t db = make_smem_desc_sw128(r_addr + (uint32_t)s * kTileBytes);
+          const uint64_t db = make_smem_desc_sw128(r_addr + (uint32_t)s * kSlotBytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            mma_bf16_ts(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
-                        (kb | k) != 0);
-          mma_commit(&empty[s]);
+          for (int k = 0; k < BK / 16; ++k) {
+            if (PAIR)
+              mma_bf16_ts_pair(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
+                               (kb | k) != 0);
+            else
+              mma_bf16_ts(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
+                          (kb | k) != 0);
+          }
+          if (PAIR) mma_commit_pair(&empty[s], 3); else mma_commit(&empty[s]);
           if (++s == NS) {
             s = 0;
             ph ^= 1u;
           }
         }
-        mma_commit(&tmem_full[buf]);
+        if (PAIR) mma_commit_pair(&tmem_full[buf], 3); else mma_commit(&tmem_full[buf]);
       }
     }
   } else {  // ---- epilogue: thread = query row, walks the 128 document scores of each finished tile ---------------
@@ -174,7 +200,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(q_full);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(q_full, 0); else mbar_arrive(q_full);
+      }
     }
     auto compact = [&]() {
       const int nmax = __reduce_max_sync(0xffffffffu, cnt);
@@ -246,7 +274,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       scan32(rb, 3);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]);
+      }
     }
     compact();
     if (q_ok) {
@@ -261,8 +291,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (PAIR) cluster_sync(); else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 __device__ __forceinline__ bool better(float s1, long long i1, float s2, long long i2) {
@@ -386,8 +418,13 @@ __global__ void __launch_bounds__(1024) compact_flags_kernel(const int* __restri
   if (threadIdx.x == 0) *qcount = s_base;
 }
 
+int scan_pair_enabled();
+int scan_stagger();
+float scan_eps();
+
 struct ScanPlan {
   int n_qtiles, S, KC, KB, stages, cap;
+  int pair;  // 1: cta_group::2 kernel, grid.x = n_qtiles rounded up to even, clusters of 2
   long long docs_per_split;
   size_t smem;
 };
@@ -395,6 +432,8 @@ struct ScanPlan {
 int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
   ScanPlan pl{};
   pl.n_qtiles = (Q + TQ - 1) / TQ;
+  pl.pair = (pl.n_qtiles >= 2 && scan_pair_enabled()) ? 1 : 0;
+  if (pl.pair) pl.n_qtiles = (pl.n_qtiles + 1) / 2 * 2;
   pl.KB = (P + BK - 1) / BK;
   const long long tiles = (N + TD - 1) / TD;
   // document splits: fill the machine when there are few query tiles, otherwise aim at whole waves
@@ -420,21 +459,22 @@ int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
   pl.S = S;
   int kc = S >= 6 ? 16 : (S >= 3 ? 32 : kMaxKC);
   while (kc < k + 6 && kc < kMaxKC) kc += 16;
-  // shared memory: resident query tile + candidate buffers + at least 3 document stages (wide P trades KC for stages)
-  size_t fixed = 0;
-  int stages = 0;
-  for (;; kc -= 16) {
-    fixed = 1024 + 512 + (size_t)(kc + kSlack) * TQ * 8;
-    stages = fixed < kSmemLimit ? (int)((kSmemLimit - fixed) / kTileBytes) : 0;
-    if (stages >= 3 || kc - 16 < k + 6 || kc <= 16) break;
-  }
+  // shared memory: candidate buffers + document slots (16 KB, or 8 KB per CTA of a pair)
+  const size_t slot = pl.pair ? kTileBytes / 2 : kTileBytes;
+  const size_t fixed = 1024 + 512 + (size_t)(kc + kSlack) * TQ * 8;
+  int stages = (int)((kSmemLimit - fixed) / slot);
   pl.KC = kc;
-  if (stages > 12) stages = 12;
+  if (stages > (pl.pair ? 16 : 12)) stages = pl.pair ? 16 : 12;
   pl.stages = stages;
-  pl.smem = fixed + (size_t)stages * kTileBytes;
+  pl.smem = fixed + (size_t)stages * slot;
   pl.cap = Q < 8192 ? Q : 8192;
   *out = pl;
   return 0;
+}
+
+int scan_pair_enabled() {
+  const char* e = getenv("TT_SCAN_PAIR");  // tuning hook: 0 forces the single-CTA kernel
+  return e ? atoi(e) : 1;
 }
 
 int scan_stagger() {
@@ -494,19 +534,37 @@ int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void
 
   static bool attr_done = false;
   if (!attr_done) {
-    TT_CUDA(cudaFuncSetAttribute(scan_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    TT_CUDA(cudaFuncSetAttribute(scan_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    TT_CUDA(cudaFuncSetAttribute(scan_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_done = true;
   }
   ScanParams sp{};
   int rc;
-  if ((rc = make_map_bf16_kmajor(&sp.d_map, Db, (uint64_t)N, P, P, TD))) return rc;
+  if ((rc = make_map_bf16_kmajor(&sp.d_map, Db, (uint64_t)N, P, P, pl.pair ? TD / 2 : TD))) return rc;
   sp.Qb = reinterpret_cast<const bf16*>(Qb);
   sp.stagger = scan_stagger();
   sp.Q = Q; sp.P = P; sp.KB = pl.KB; sp.KC = pl.KC; sp.stages = pl.stages;
   sp.N = N; sp.docs_per_split = pl.docs_per_split;
   sp.cand_s = w.cand_s; sp.cand_i = w.cand_i; sp.bound = w.bound;
-  scan_candidates_kernel<<<dim3(pl.n_qtiles, pl.S), kScanThreads, pl.smem, st>>>(sp);
-  TT_LAUNCH_CHECK();
+  if (pl.pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.n_qtiles, pl.S);
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TT_CUDA(cudaLaunchKernelEx(&cfg, scan_candidates_kernel<true>, sp));
+    note_launch();
+  } else {
+    scan_candidates_kernel<false><<<dim3(pl.n_qtiles, pl.S), kScanThreads, pl.smem, st>>>(sp);
+    TT_LAUNCH_CHECK();
+  }
 
   const int C = pl.S * pl.KC;
   const long long warps = (long long)Q * ((C + kGroup - 1) / kGroup);
