@@ -10,10 +10,11 @@ baseline (the oracle port of the reference's fp32 step, oracle/two_towers_oracle
 Workload (BASELINE.json configs[1], "heavy GPU run shape"): per-GPU batch 2048 triplets, projection dim 512,
 margin 0.3, query length 32 / document length 256 tokens (SURVEY.md §8d shape U: full-length rows, ids
 uniform in [999, 30522) — the roofline case), random-init 30522x384 tables, Adam lr 1e-3.  Weak scaling:
-every rank processes its own 2048-triplet batch, one NCCL all-reduce of the flat projection gradient per step.
+every rank processes its own 2048-triplet batch; the one exchange per step is a fused reduce-scatter -> Adam ->
+all-gather kernel over NVLink peer memory (TT_DP_EXCHANGE=nccl selects all-reduce + Adam instead).
 
 A "step" = H2D'd tokens -> pooled gather (q,p,n) -> both tower MLPs -> cosine triplet loss -> all gradients
--> [all-reduce] -> Adam.  Prints ONE JSON line on rank 0.
+-> [gradient exchange +] Adam.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -263,8 +264,8 @@ def run_b200(args):
             ready[i] = torch.cuda.Event()
             ready[i].record(copy_stream)
         main.wait_event(ready[i])
-        loss = trainer.step(slot)
-        loss_host[i: i + 1].copy_(loss.reshape(1), non_blocking=True)
+        trainer.step(slot)
+        trainer.read_loss_async(loss_host[i: i + 1])
         done[i] = torch.cuda.Event()
         done[i].record(main)
 
@@ -330,6 +331,9 @@ def run_b200(args):
                "sample": f"{info['steps']} fp32 steps of {info['batch']} triplets in {info['seconds']} s "
                          f"(oracle/two_towers_oracle.train_step, torch CPU, {info['cores']} threads)"}
 
+    exchange_kind = trainer.exchange
+    barrier()
+    trainer.close()
     scan = None
     if not args.no_scan:
         del trainer, model
@@ -341,7 +345,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else f"f32 ({args.precision} tensor-core projection)",
-            "data": "synthetic", "config": workload_config(world, args.precision, args.table_dtype),
+            "data": "synthetic", "config": workload_config(world, args.precision, args.table_dtype) | {"dp_exchange": exchange_kind},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": launches_per_step * K, "gpu_launches_per_step": launches_per_step,

@@ -158,7 +158,12 @@ typedef struct tt_step_args {
   int precision;
   void* ws; size_t ws_bytes;  /* >= tt_step_ws_bytes(...); zero-fill it once before its first use (it holds an
                                  arrival counter that every call leaves at zero again)                        */
+  int phases;        /* 0 = whole step; TT_STEP_FRONT = pooled gather only (reads tokens + tables, not the
+                        projection weights, so it may overlap the previous step's parameter exchange);
+                        TT_STEP_BACK = everything after it, on the same workspace                             */
 } tt_step_args;
+#define TT_STEP_FRONT 1
+#define TT_STEP_BACK 2
 size_t tt_step_ws_bytes(int B, int Lq, int Ld, int H, int P, int vocab, int precision,
                         int train_table);
 int tt_triplet_step(const tt_step_args* args, tt_stream_t stream);
@@ -217,6 +222,47 @@ int tt_topk_merge(const float* parts_score, const int64_t* parts_id, int G, int 
  * kk <= k evaluates NDCG@kk from the first kk entries. */
 int tt_ndcg_at_k(const int64_t* top_id, int Q, int k, int kk, const int64_t* rel_offsets,
                  const int64_t* rel_ids, double* ndcg, tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data parallelism over NVLink peer memory (the reference is single-device, this is the one
+ * exchange a data-parallel training.py:47-51 needs).  One process per GPU; segments are exchanged as CUDA IPC
+ * handles (the host side ships the 64 handle bytes through torch.distributed).  These four calls are the only
+ * ones that allocate: IPC needs memory whose allocation base the library knows.
+ * ---------------------------------------------------------------------------------------- */
+#define TT_PEER_HANDLE_BYTES 64
+int tt_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out /* TT_PEER_HANDLE_BYTES */); /* zero-filled */
+int tt_peer_open(const void* handle, void** dev_ptr); /* maps a peer's segment into this process */
+int tt_peer_close(void* dev_ptr);
+int tt_peer_free(void* dev_ptr);
+
+/* Segment layout for n_param fp32 parameters on `world` ranks (S = slice = ceil((n_param+1)/world) rounded up to 64):
+ *   floats [0, world*S)            the parameters, slot [n_param] = the step's global loss
+ *   floats [world*S, 2*world*S)    gradient landing zone [source rank][S]
+ *   then 256 bytes of flags        grad-arrived[world] | param-arrived[world]
+ * The caller points its flat parameter tensor at offset 0 of its own segment. */
+size_t tt_dp_segment_bytes(size_t n_param, int world);
+
+/* ONE kernel: reduce-scatter of the flat gradient (+ loss in slot n_param) over peer stores, torch.optim.Adam
+ * arithmetic (training.py:436 defaults) on this rank's slice, all-gather of the new parameters into every rank's
+ * segment.  Sums run in rank order, so all ranks hold bit-identical parameters and a run is bit-reproducible.
+ *   segments[world]: every rank's segment as mapped in THIS process (own entry = the local pointer);
+ *   grad [n_param+1] local; exp_avg / exp_avg_sq [n_param] local (only this rank's slice is touched);
+ *   state: 4 doubles {t, beta1^t, beta2^t, -}; ctl: 4 u32 {epoch, ticket, ticket, error}, both zero-initialised,
+ *   local.  ctl[3] != 0 after a call means a peer did not answer within 4 s.
+ *   max_ctas: upper bound on the CTAs used (<= SM count; 0 = default 64) — every CTA spins on peer flags, so
+ *   the grid must be co-resident with whatever else runs concurrently. */
+int tt_dp_reduce_adam(void* const* segments, int world, int rank, size_t n_param, const float* grad,
+                      float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                      double* state, unsigned* ctl, int max_ctas, tt_stream_t stream);
+
+/* Barrier across the ranks on `stream`: flags[r] = rank r's flag array (>= world u32, zero-initialised, peer
+ * memory), ctl as above (its own 4 u32). */
+int tt_peer_barrier(void* const* flags, int world, int rank, unsigned* ctl, tt_stream_t stream);
+
+/* tt_topk_merge reading every shard's [Q,k] list in place from its owner's peer memory (corpus scan, §8e);
+ * bracket it with tt_peer_barrier so the lists are complete before and not overwritten during the merge. */
+int tt_peer_topk_merge(const float* const* parts_score, const int64_t* const* parts_id, int world, int Q, int k,
+                       float* top_score, int64_t* top_id, tt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -350,6 +350,79 @@ def test_adam_kernel_matches_torch_adam(tt):
 
 
 # ---------------------------------------------------------------------------------------------------
+# data-parallel exchange: fused reduce-scatter -> Adam -> all-gather over peer memory (tt_dp_reduce_adam)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,n", [(1, 5000), (2, 919552), (4, 57600), (8, 919552), (3, 1001)])
+def test_dp_exchange_virtual_ranks_match_summed_adam(tt, world, n):
+    """`world` ranks on ONE device (own streams, plain pointers instead of IPC mappings) run the real protocol:
+    every rank must end with bit-identical parameters == Adam applied to the rank-ordered sum of the gradients."""
+    from two_towers_overlords_b200 import comm
+
+    torch.manual_seed(world)
+    xs = comm.DpExchange.virtual_ranks(n, world, DEV)
+    p0 = torch.randn(n, device=DEV)
+    for x in xs:
+        x.flat_p.copy_(p0)
+    ms = [torch.zeros(n, device=DEV) for _ in xs]
+    vs = [torch.zeros(n, device=DEV) for _ in xs]
+    streams = [torch.cuda.Stream() for _ in xs]
+    ref_p, ref_m, ref_v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    torch.cuda.synchronize()
+    try:
+        for step in range(1, 4):
+            grads = [torch.randn(n + 1, device=DEV) * 0.1 for _ in xs]
+            total = grads[0].clone()
+            for g in grads[1:]:
+                total += g  # rank order, fp32: what the kernel does
+            torch.cuda.synchronize()
+            for x, g, m, v, st in zip(xs, grads, ms, vs, streams):
+                with torch.cuda.stream(st):
+                    x.reduce_adam(g, m, v, 3e-3, max_ctas=16)
+            torch.cuda.synchronize()
+            for x in xs:
+                x.check()
+            tt.ops.adam_step(ref_p, total[:n].contiguous(), ref_m, ref_v, 3e-3, step)
+            for x in xs:
+                assert torch.equal(x.flat_p, xs[0].flat_p)       # replicas stay bit-identical
+                assert torch.equal(x.loss, total[n:])            # loss slot = sum of the ranks' loss terms
+            assert max_rel(xs[0].flat_p, ref_p, 1e-3) < 1e-6
+        # Adam moments are sharded: rank r owns slice r, together they cover the reference moments
+        S = (((n + 1 + world - 1) // world) + 63) // 64 * 64
+        m_all = torch.cat([ms[r][r * S: min((r + 1) * S, n)] for r in range(world) if r * S < n])
+        assert max_rel(m_all, ref_m, 1e-6) < 1e-6
+    finally:
+        for x in xs:
+            x.close()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_trainer_peer_exchange_equals_plain_adam(tt, use_graph):
+    """world = 1: the split step (pooled gather | rest) + exchange kernel on the side stream must reproduce the
+    single-graph trainer bit for bit."""
+    B, Lq, Ld, P, V = 256, 16, 64, 128, 4096
+    batches = [O.synth_triplet_batch(B, Lq, Ld, "U", seed=20 + i, vocab=V) for i in range(3)]
+    out = []
+    for exchange in (None, "peer"):
+        torch.manual_seed(4)
+        m = tt.TwoTowersModel(projection_dim=P, vocab_size=V, precision="bf16x3").to(DEV)
+        tr = tt.training.FusedTrainer(m, 0.3, 1e-3, B, Lq, Ld, precision="bf16x3", use_graph=use_graph,
+                                      ids_dtype=torch.int64, mask_dtype=torch.int64, exchange=exchange)
+        losses = []
+        for b in batches:
+            for dst, src in zip(tr.tok, b.astuple()):
+                dst.copy_(src)
+            tr.step()
+            tr.wait()
+            losses.append(float(tr.loss_view[0].item()))
+        torch.cuda.synchronize()
+        out.append((tr.flat_p.clone(), losses))
+        tr.close()
+        assert m.query_tower.projection[0].weight.data_ptr() != 0
+    assert out[0][1] == out[1][1]
+    assert torch.equal(out[0][0], out[1][0])
+
+
+# ---------------------------------------------------------------------------------------------------
 # retrieval
 # ---------------------------------------------------------------------------------------------------
 def _check_topk(top_s, top_i, scores64, k):

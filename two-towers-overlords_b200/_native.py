@@ -55,6 +55,7 @@ class StepArgs(ctypes.Structure):
         ("err_flag", c_void_p),
         ("precision", c_int),
         ("ws", c_void_p), ("ws_bytes", c_size_t),
+        ("phases", c_int),
     ]
 
 
@@ -94,6 +95,16 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p]),
     "tt_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_ndcg_at_k": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tt_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "tt_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "tt_peer_close": (c_int, [c_void_p]),
+    "tt_peer_free": (c_int, [c_void_p]),
+    "tt_dp_segment_bytes": (c_size_t, [c_size_t, c_int]),
+    "tt_dp_reduce_adam": (c_int, [POINTER(c_void_p), c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_float,
+                                  c_float, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "tt_peer_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
+    "tt_peer_topk_merge": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

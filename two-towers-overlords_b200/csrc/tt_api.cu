@@ -225,8 +225,11 @@ extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
   pp.err = a->err_flag;
 
   float* dxhat = train_table ? w.dxhat : nullptr;
+  TT_REQUIRE(a->phases >= 0 && a->phases <= (TT_STEP_FRONT | TT_STEP_BACK), "tt_triplet_step: bad phases %d", a->phases);
+  const bool front = a->phases == 0 || (a->phases & TT_STEP_FRONT), back = a->phases == 0 || (a->phases & TT_STEP_BACK);
   if (a->precision == TT_PREC_FP32) {
-    if ((rc = pool_fwd_launch(pp, a->table_dtype, H, st))) return rc;
+    if (front && (rc = pool_fwd_launch(pp, a->table_dtype, H, st))) return rc;
+    if (!back) return 0;
     // 2. both towers
     if ((rc = mlp_fwd_fp32(w.xhat, B, H, P, a->Wq1, a->bq1, a->Wq2, a->bq2, w.h, w.y, st))) return rc;
     if ((rc = mlp_fwd_fp32(w.xhat + (size_t)B * H, 2 * B, H, P, a->Wd1, a->bd1, a->Wd2, a->bd2, w.h + (size_t)B * P,
@@ -263,7 +266,9 @@ extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
     s.dxhat = dxhat;
     s.n_split = (a->precision == TT_PREC_BF16X3) ? 3 : 1;
     s.ws = w.mma_ws; s.ws_bytes = w.mma_ws_bytes;
+    s.phases = a->phases;
     if ((rc = step_sm100(s, st))) return rc;
+    if (!back) return 0;
   }
   // 6. table gradients (D2 extension)
   if (train_table) {

@@ -651,10 +651,14 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
   const int row0[2] = {0, B}, rows[2] = {B, 2 * B}, tcol[2] = {0, w.dcol};
 
   // 1. pooled gather: fp32 xhat + its bf16 split (row-major); the transposed copy comes from a tiled transpose
-  PoolParams pp = s.pool;
-  pp.x_hi = w.x_hi; pp.x_lo = w.x_lo; pp.x_lo2 = (np == 3) ? w.x_lo2 : nullptr; pp.xt_hi = nullptr; pp.xt_lo = nullptr;
-  if ((rc = pool_fwd_launch(pp, s.table_dtype, H, st))) return rc;
-  if ((rc = transpose_pair(w.x_hi, w.x_lo, 3 * B, H, w.xt_hi, w.xt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
+  const bool front = s.phases == 0 || (s.phases & TT_STEP_FRONT), back = s.phases == 0 || (s.phases & TT_STEP_BACK);
+  if (front) {
+    PoolParams pp = s.pool;
+    pp.x_hi = w.x_hi; pp.x_lo = w.x_lo; pp.x_lo2 = (np == 3) ? w.x_lo2 : nullptr; pp.xt_hi = nullptr; pp.xt_lo = nullptr;
+    if ((rc = pool_fwd_launch(pp, s.table_dtype, H, st))) return rc;
+    if ((rc = transpose_pair(w.x_hi, w.x_lo, 3 * B, H, w.xt_hi, w.xt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
+  }
+  if (!back) return 0;
   // 2. weights of both towers -> bf16 terms (+ transposes for the backward contractions), one launch
   {
     SplitJob jobs[4];

@@ -25,6 +25,7 @@ struct StepSm100 {
   int n_split;                // 3 = bf16x3, 1 = bf16
   void* ws;
   size_t ws_bytes;
+  int phases;                 // 0 / TT_STEP_FRONT | TT_STEP_BACK
 };
 size_t step_sm100_ws_bytes(int B, int H, int P, int train_table);
 int step_sm100(const StepSm100& s, cudaStream_t st);

@@ -257,8 +257,12 @@ class TripletStep:
         self._keep.append(tokens)
         return len(self.slots) - 1
 
-    def run(self, slot: int = 0):
-        N.check(self.lib.tt_triplet_step(ctypes.byref(self.slots[slot]), N.stream()), "tt_triplet_step")
+    def run(self, slot: int = 0, phases: int = 0):
+        """phases: 0 = whole step, 1 = pooled gather only (TT_STEP_FRONT), 2 = the rest (TT_STEP_BACK)."""
+        a = self.slots[slot]
+        a.phases = int(phases)
+        N.check(self.lib.tt_triplet_step(ctypes.byref(a), N.stream()), "tt_triplet_step")
+        a.phases = 0
         return self.loss
 
 

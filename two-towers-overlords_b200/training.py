@@ -15,6 +15,7 @@ Additions (the B200 path proper):
 from __future__ import annotations
 
 import math
+import os
 import random
 from typing import Optional, Union
 
@@ -23,10 +24,11 @@ import torch
 from torch import GradScaler, autocast
 
 try:
-    from . import ops
+    from . import comm, ops
     from .data import MSMarcoDataset, TokenTripletLoader, TripletDataLoader
     from .model import TokenBatch, TripletLoss, TwoTowersModel
 except ImportError:
+    import comm
     import ops
     from data import MSMarcoDataset, TokenTripletLoader, TripletDataLoader
     from model import TokenBatch, TripletLoss, TwoTowersModel
@@ -122,7 +124,8 @@ class FusedTrainer:
     def __init__(self, model: TwoTowersModel, margin: float, lr: float, batch_size: int, Lq: int = 32, Ld: int = 256,
                  precision: Optional[str] = None, world_size: int = 1, rank: int = 0, use_graph: bool = True,
                  betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, ids_dtype=torch.int32,
-                 mask_dtype=torch.uint8, token_slots: int = 1):
+                 mask_dtype=torch.uint8, token_slots: int = 1, exchange: Optional[str] = None,
+                 exchange_ctas: int = 0):
         qt, dt = model.query_tower, model.document_tower
         self.model = model
         self.device = qt.pretrained_model.device
@@ -140,7 +143,26 @@ class FusedTrainer:
         sizes = [p.numel() for p in params]
         self.n_param = sum(sizes)
         dev = self.device
-        self.flat_p = torch.empty(self.n_param, dtype=torch.float32, device=dev)
+        # data-parallel exchange: "peer" = ONE kernel (reduce-scatter over NVLink peer stores -> Adam on the local
+        # slice -> all-gather of the new parameters), overlapped with the next step's pooled gather, which does not
+        # read the projection weights; "nccl" = all-reduce + Adam launch, serialised (the baseline)
+        if world_size > 1:
+            self.exchange = exchange or os.environ.get("TT_DP_EXCHANGE", "peer")
+        else:  # one rank: the fused exchange kernel still works (used by tests), the default is the plain Adam launch
+            self.exchange = "peer" if exchange == "peer" else "none"
+        if self.exchange not in ("none", "peer", "nccl"):
+            raise ValueError(f"exchange must be 'peer' or 'nccl', got {self.exchange!r}")
+        self.exchange_ctas = int(exchange_ctas or os.environ.get("TT_DP_CTAS", "0"))
+        self.xchg = None
+        if self.exchange == "peer":
+            self.xchg = comm.DpExchange(self.n_param, world_size, rank, dev, group=process_group)
+            self.flat_p = self.xchg.flat_p
+            self.side = torch.cuda.Stream(device=dev, priority=-1)
+            self.ev_back = torch.cuda.Event()
+            self.ev_xchg = torch.cuda.Event()
+            self._xchg_pending = False
+        else:
+            self.flat_p = torch.empty(self.n_param, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(self.n_param + 1, dtype=torch.float32, device=dev)  # [+1]: loss
         self.exp_avg = torch.zeros(self.n_param, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.n_param, dtype=torch.float32, device=dev)
@@ -155,7 +177,9 @@ class FusedTrainer:
                 self.p_views.append(view)
                 self.g_views.append(self.flat_g[off: off + n].view_as(p))
                 off += n
-        self.loss_view = self.flat_g[self.n_param:]
+        # where the step's GLOBAL loss can be read: slot n of the flat gradient (summed in place by NCCL), or slot n
+        # of the peer segment (written by the exchange kernel)
+        self.loss_view = self.xchg.loss if self.xchg is not None else self.flat_g[self.n_param:]
         # static token buffers (graph replays read these addresses)
         mk = lambda L, dt_: torch.zeros(batch_size, L, dtype=dt_, device=dev)  # noqa: E731
         new_set = lambda: (mk(Lq, ids_dtype), mk(Lq, mask_dtype), mk(Ld, ids_dtype), mk(Ld, mask_dtype),  # noqa: E731
@@ -170,7 +194,7 @@ class FusedTrainer:
                                 torch.zeros_like(dt.pretrained_model.table, dtype=torch.float32))
         self.step_obj = ops.TripletStep(batch_size, Lq, Ld, self.H, self.P, self.vocab, self.precision, dev,
                                         train_table=self.train_table)
-        self.step_obj.loss = self.loss_view  # loss lands in the flat gradient buffer's last slot
+        self.step_obj.loss = self.flat_g[self.n_param:]  # this rank's loss term lands in the flat gradient's last slot
         self.step_obj.bind(self.tok, (qt.pretrained_model.table.data, dt.pretrained_model.table.data), self.p_views,
                            self.g_views, self.margin, 1.0 / (batch_size * world_size), 1.0, self.table_grads)
         for toks in self.tok_slots[1:]:
@@ -188,8 +212,32 @@ class FusedTrainer:
                                                    n.input_ids, n.attention_mask)):
             dst.copy_(src, non_blocking=True)
 
-    def _fwd_bwd(self, slot: int = 0):
-        self.step_obj.run(slot)
+    def _fwd_bwd(self, slot: int = 0, phases: int = 0):
+        self.step_obj.run(slot, phases)
+
+    def _exchange(self):
+        """Peer mode: the fused reduce-scatter / Adam / all-gather kernel on the high-priority side stream."""
+        self.ev_back.record()
+        self.side.wait_event(self.ev_back)
+        with torch.cuda.stream(self.side):
+            self.xchg.reduce_adam(self.flat_g, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps,
+                                  self.exchange_ctas)
+            self.ev_xchg.record()
+        self._xchg_pending = True
+
+    def wait(self):
+        """Makes the current stream wait for the last step's parameter exchange (peer mode runs it on a side
+        stream so that it overlaps the next step's pooled gather).  Call before reading parameters or the loss."""
+        if self.xchg is not None and self._xchg_pending:
+            torch.cuda.current_stream().wait_event(self.ev_xchg)
+
+    def read_loss_async(self, host_dst: torch.Tensor):
+        """Copies the last step's global loss into pinned host memory without stalling the step pipeline."""
+        if self.xchg is not None:
+            with torch.cuda.stream(self.side):
+                host_dst.copy_(self.loss_view.reshape(host_dst.shape), non_blocking=True)
+        else:
+            host_dst.copy_(self.loss_view.reshape(host_dst.shape), non_blocking=True)
 
     def _optimizer(self):
         b1, b2 = self.betas
@@ -210,6 +258,15 @@ class FusedTrainer:
         lib = ops.N.load()
         for slot in range(len(self.tok_slots)):
             n0 = lib.tt_launch_count()
+            if self.xchg is not None:  # two graphs per slot: the exchange of the previous step overlaps the first
+                gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gf):
+                    self._fwd_bwd(slot, 1)
+                with torch.cuda.graph(gb):
+                    self._fwd_bwd(slot, 2)
+                self.graph_fb[slot] = (gf, gb)
+                self.kernel_launches_per_step = lib.tt_launch_count() - n0 + 1
+                continue
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._fwd_bwd(slot)
@@ -217,7 +274,7 @@ class FusedTrainer:
                     self._optimizer()
             self.graph_fb[slot] = g
             self.kernel_launches_per_step = lib.tt_launch_count() - n0
-        if self.world > 1:
+        if self.world > 1 and self.xchg is None:
             n0 = lib.tt_launch_count()
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt):
@@ -227,9 +284,26 @@ class FusedTrainer:
     def step(self, slot: int = 0) -> torch.Tensor:
         """One optimiser step on the tokens currently in the static buffers of `slot`; returns the (global)
         loss as a device scalar — no host sync."""
-        if self.use_graph:
-            if self.graph_fb[0] is None:
-                self._capture()  # warm-up runs forward/backward only, capture itself executes nothing
+        if self.use_graph and self.graph_fb[0] is None:
+            self._capture()  # warm-up runs forward/backward only, capture itself executes nothing
+        if self.xchg is not None:
+            # pooled gather of THIS step (tokens + frozen tables only) may run while the previous step's exchange
+            # is still landing parameters; everything after it waits for the exchange
+            lib = ops.N.load()
+            n0 = lib.tt_launch_count()
+            if self.use_graph:
+                self.graph_fb[slot][0].replay()
+            else:
+                self._fwd_bwd(slot, 1)
+            self.wait()
+            if self.use_graph:
+                self.graph_fb[slot][1].replay()
+            else:
+                self._fwd_bwd(slot, 2)
+            self._exchange()
+            if not self.use_graph:
+                self.kernel_launches_per_step = lib.tt_launch_count() - n0
+        elif self.use_graph:
             self.graph_fb[slot].replay()
             if self.world > 1:
                 torch.distributed.all_reduce(self.flat_g, group=self.pg)
@@ -245,12 +319,31 @@ class FusedTrainer:
         self.steps_done += 1
         return self.loss_view[0]
 
+    def close(self):
+        """Releases the peer segment (collective in peer mode: call on every rank after a barrier)."""
+        if self.xchg is not None:
+            torch.cuda.synchronize()
+            self.xchg.check()
+            # parameters move back to ordinary torch memory so the model outlives the segment
+            with torch.no_grad():
+                keep = self.flat_p.clone()
+                off = 0
+                for p in self.model.projection_parameters():
+                    p.data = keep[off: off + p.numel()].view_as(p)
+                    off += p.numel()
+            self.flat_p = keep
+            self.loss_view = self.loss_view.clone()
+            self.xchg.close()
+            self.xchg = None
+            self.exchange = "closed"
+
     def train_epoch(self, loader: TokenTripletLoader, log_every: int = 0) -> float:
         total = torch.zeros((), dtype=torch.float64, device=self.device)
         nb = 0
         for q, p, n in loader:
             self.load_tokens(q, p, n)
             loss = self.step()
+            self.wait()
             total += loss.double()
             nb += 1
             if log_every and nb % log_every == 0:
