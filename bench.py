@@ -206,9 +206,10 @@ def run_b200(args):
                            token_slots=N_TOKEN_SETS)
     host_sets = token_sets(N_TOKEN_SETS, B_PER_GPU, 1234 + rank, ids_dtype, mask_dtype, pin=True)
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_sets[0])
-    for slot, hs in enumerate(host_sets):  # inputs resident in HBM for the `value` leg
-        for dst, src in zip(trainer.tok_slots[slot], hs):
-            dst.copy_(src, non_blocking=True)
+    host_packed = [trainer.pack_host_tokens(hs) for hs in host_sets]  # one pinned buffer per batch: one H2D copy
+    h2d_bytes = host_packed[0].numel()
+    for slot, hp in enumerate(host_packed):  # inputs resident in HBM for the `value` leg
+        trainer.load_packed(hp, slot)
     torch.cuda.synchronize()
 
     def barrier():
@@ -226,6 +227,7 @@ def run_b200(args):
     K, W = args.steps, args.warmup
     for i in range(W):
         trainer.step(i % N_TOKEN_SETS)
+    trainer.wait()
     barrier()
     launches_per_step = int(trainer.kernel_launches_per_step or 0)
 
@@ -238,6 +240,7 @@ def run_b200(args):
     ev0.record()
     for i in range(K):
         trainer.step((W + i) % N_TOKEN_SETS)
+    trainer.wait()  # peer mode: the last step's exchange (the others ran under the following step's gather)
     ev1.record()
     barrier()
     t_wall1 = time.time()
@@ -250,24 +253,21 @@ def run_b200(args):
     # every step: pinned host tokens -> H2D (copy stream, two steps ahead at most) -> FusedTrainer.step -> loss D2H
     copy_stream = torch.cuda.Stream()
     main = torch.cuda.current_stream()
-    loss_host = torch.zeros(K + W, dtype=torch.float32).pin_memory()
-    done = [None] * (K + W)
-    ready = [None] * (K + W)
+    loss_host = torch.zeros(K + W + 1, dtype=torch.float32).pin_memory()
+    done = [torch.cuda.Event() for _ in range(4)]
+    ready = [torch.cuda.Event() for _ in range(4)]
 
     def e2e_step(i):
         slot = i % N_TOKEN_SETS
-        if i >= 2 and done[i - 2] is not None:
-            copy_stream.wait_event(done[i - 2])  # bounded prefetch; slot reuse is N_TOKEN_SETS steps away
+        if i >= 2:
+            copy_stream.wait_event(done[(i - 2) % 4])  # bounded prefetch; slot reuse is N_TOKEN_SETS steps away
         with torch.cuda.stream(copy_stream):
-            for dst, src in zip(trainer.tok_slots[slot], host_sets[slot]):
-                dst.copy_(src, non_blocking=True)
-            ready[i] = torch.cuda.Event()
-            ready[i].record(copy_stream)
-        main.wait_event(ready[i])
+            trainer.load_packed(host_packed[slot], slot)
+            ready[i % 4].record(copy_stream)
+        main.wait_event(ready[i % 4])
         trainer.step(slot)
-        trainer.read_loss_async(loss_host[i: i + 1])
-        done[i] = torch.cuda.Event()
-        done[i].record(main)
+        trainer.read_loss_async(loss_host[i: i + 1])  # peer mode: the previous step's loss (exchange is pipelined)
+        done[i % 4].record(main)
 
     for i in range(W):
         e2e_step(i)
@@ -276,6 +276,8 @@ def run_b200(args):
     ev0.record()
     for i in range(W, W + K):
         e2e_step(i)
+    trainer.wait()
+    trainer.read_loss_async(loss_host[W + K: W + K + 1])
     ev1.record()
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))

@@ -21,19 +21,21 @@ from two_towers_overlords_b200.training import FusedTrainer  # noqa: E402
 
 B, Lq, Ld, P, V, STEPS = 512, 32, 128, 256, 30522, 6
 res = {}
-for exchange in ("nccl", "peer"):
+for exchange in ("nccl", "peer", "peer-pipelined"):
     torch.manual_seed(0)
     model = TwoTowersModel(projection_dim=P, vocab_size=V, precision="bf16x3").to(dev)
     tr = FusedTrainer(model, 0.3, 1e-3, B, Lq, Ld, precision="bf16x3", world_size=world, rank=rank,
-                      ids_dtype=torch.int64, mask_dtype=torch.int64, exchange=exchange)
+                      ids_dtype=torch.int64, mask_dtype=torch.int64, exchange=exchange.split("-")[0])
     losses = []
     for i in range(STEPS):
         b = O.synth_triplet_batch(B, Lq, Ld, "U", seed=100 * i + rank, vocab=V)
         for dst, src in zip(tr.tok, b.astuple()):
             dst.copy_(src)
         tr.step()
-        tr.wait()
-        losses.append(float(tr.loss_view[0].item()))
+        if exchange != "peer-pipelined":
+            tr.wait()
+            losses.append(float(tr.loss_view[0].item()))
+    tr.wait()
     torch.cuda.synchronize()
     p = tr.flat_p.clone()
     # replicas identical?
@@ -52,6 +54,8 @@ if rank == 0:
     print(f"world={world} replicas identical: nccl={sn} peer={sp}; |p_peer - p_nccl|/|p| = {err:.3e}")
     print("loss nccl:", [f"{x:.6f}" for x in ln])
     print("loss peer:", [f"{x:.6f}" for x in lp])
+pq, lq, sq = res["peer-pipelined"]
+assert sq and torch.equal(pq, pp), "pipelined peer exchange differs from the step-by-step one"
 assert sp, "peer exchange left the replicas different"
 assert err < 1e-5, err
 assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(ln, lp))

@@ -8,7 +8,8 @@
 //      tcgen05.ld (thread = query, columns = documents) and keep the KC best (approximate score, doc) per query
 //      in shared memory behind a register threshold — an insertion happens ~KC*ln(n/KC) times per query, so the
 //      epilogue is one compare per score and hides under the MMAs of the next tile.
-//   2. rescore_select_kernel — exact fp32 dot products (CUDA cores) of the S*KC candidates of each query, top-k by
+//   2. refine_kernel — drops candidates whose approximate score is more than 2 eps below the k-th best approximate
+//      score (they provably cannot enter the top k), exact fp32 dot products (CUDA cores) of the rest, top-k by
 //      (score desc, id asc), plus a completeness proof: every non-candidate of split s has approximate score <=
 //      bound_s (the KC-th best of that split), and |approx - exact| <= eps for unit-norm rows, so the list is
 //      exact if max_s bound_s + eps < k-th exact score.  Queries that fail the proof are listed and re-scanned
@@ -243,18 +244,30 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       const uint32_t t_addr = tmem_base + (uint32_t)(buf * TD) + ((uint32_t)(qd * 32) << 16);
       uint32_t ra[32], rb[32];
       auto scan32 = [&](const uint32_t* r, int c) {
-        float m = __uint_as_float(r[0]);
+        // group maxima first (four independent 8-long chains instead of one 32-long one); on a hit only the
+        // groups that hold a score above the threshold are walked
+        float gm[4];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-        if (m > thr) {  // rare once the threshold has settled
+        for (int g = 0; g < 4; ++g) {
+          float m = __uint_as_float(r[g * 8]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int dj = c * 32 + j;
-            const float vj = __uint_as_float(r[j]);
-            if (vj > thr && dj < nd) {
-              ls[cnt * TQ] = vj;
-              li[cnt * TQ] = d0 + dj;
-              ++cnt;
+          for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(r[g * 8 + j]));
+          gm[g] = m;
+        }
+        if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) > thr) {  // rare once the threshold has settled
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (gm[g] > thr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int dj = c * 32 + g * 8 + j;
+                const float vj = __uint_as_float(r[g * 8 + j]);
+                if (vj > thr && dj < nd) {
+                  ls[cnt * TQ] = vj;
+                  li[cnt * TQ] = d0 + dj;
+                  ++cnt;
+                }
+              }
             }
           }
         }
@@ -301,62 +314,147 @@ __device__ __forceinline__ bool better(float s1, long long i1, float s2, long lo
   return s1 > s2 || (s1 == s2 && i1 < i2);
 }
 
-// exact fp32 dot products of the candidates: one warp per (query, group of kGroup candidates), query row in registers
-constexpr int kGroup = 32;
-__global__ void __launch_bounds__(128)
-    rescore_kernel(const float* __restrict__ Qn, const float* __restrict__ Dn, const int* __restrict__ cand_i, int S,
-                   int Q, int KC, int P, float* __restrict__ exact) {
-  const int C = S * KC;
-  const int groups = (C + kGroup - 1) / kGroup;
-  const long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= (long long)Q * groups) return;
-  const int q = (int)(w / groups), g = (int)(w - (long long)q * groups);
-  float qv[16];  // P <= 512
-  const float* qr = Qn + (size_t)q * P;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) qv[i] = (lane + 32 * i < P) ? qr[lane + 32 * i] : 0.f;
-  const int c1 = min(C, (g + 1) * kGroup);
-  for (int c = g * kGroup; c < c1; ++c) {
+// Refinement of one query's S*KC candidates (one CTA per query):
+//   a. tk = k-th best APPROXIMATE score among the candidates; since |approx - exact| <= eps, the k documents that
+//      lead by approximate score all have exact score >= tk - eps, so the k-th best exact score is >= tk - eps;
+//   b. a candidate with approx < tk - 2 eps has exact < tk - eps and can never enter the top k: only candidates
+//      at or above t = tk - 2 eps are re-scored exactly (a few dozen instead of S*KC row gathers);
+//   c. exact fp32 dot products (one warp per candidate, the same lane-strided fmaf chain as the fp32 scan),
+//      top-k by (score desc, id asc);
+//   d. completeness proof against the documents that never became candidates: every such document of split s
+//      has approx <= bound_s, so the list is exact if max_s bound_s + eps < k-th exact score.  Queries that fail
+//      (or select more than kSelCap candidates) are flagged for the exact fp32 re-scan.
+constexpr int kSelCap = 256;
+constexpr int kRefineThreads = 128;
+__global__ void __launch_bounds__(kRefineThreads)
+    refine_kernel(const float* __restrict__ Qn, const float* __restrict__ Dn, const float* __restrict__ cand_s,
+                  const int* __restrict__ cand_i, const float* __restrict__ bound, int S, int Q, int KC, int P, int k,
+                  long long id_base, float eps, float* __restrict__ top_score, long long* __restrict__ top_id,
+                  int* __restrict__ flag) {
+  extern __shared__ float approx[];  // [C]
+  __shared__ float red_v[4];
+  __shared__ int red_c[4];
+  __shared__ int sel_c[kSelCap];
+  __shared__ float sel_s[kSelCap];
+  __shared__ int sel_id[kSelCap];
+  __shared__ int n_sel;
+  __shared__ float s_last_v, s_bmax;
+  __shared__ int s_last_c, s_found;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = blockIdx.x, C = S * KC;
+  for (int c = tid; c < C; c += kRefineThreads) {
     const int s = c / KC, j = c - s * KC;
-    const int id = cand_i[((size_t)s * Q + q) * KC + j];  // warp-uniform
-    float dot = 0.f;
-    if (id >= 0) {
-      const float* dr = Dn + (size_t)id * P;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (lane + 32 * i < P) dot = fmaf(qv[i], __ldg(dr + lane + 32 * i), dot);
-      dot = warp_sum(dot);
-    }
-    if (lane == 0) exact[(size_t)q * C + c] = dot;
+    const size_t idx = ((size_t)s * Q + q) * KC + j;
+    approx[c] = cand_i[idx] >= 0 ? cand_s[idx] : -INFINITY;
   }
-}
-
-// one warp per query: top-k of the exactly scored candidates + completeness proof
-__global__ void __launch_bounds__(128)
-    select_kernel(const float* __restrict__ exact, const int* __restrict__ cand_i, const float* __restrict__ bound, int S,
-                  int Q, int KC, int k, long long id_base, float eps, float* __restrict__ top_score,
-                  long long* __restrict__ top_id, int* __restrict__ flag) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 4 + warp;
-  if (q >= Q) return;
-  const int C = S * KC;
-  const float* sc = exact + (size_t)q * C;
-  float bmax = -INFINITY;
-  for (int s = lane; s < S; s += 32) bmax = fmaxf(bmax, bound[(size_t)s * Q + q]);
+  float bm = -INFINITY;
+  for (int s = tid; s < S; s += kRefineThreads) bm = fmaxf(bm, bound[(size_t)s * Q + q]);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+  for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+  if (lane == 0) red_v[warp] = bm;
+  if (tid == 0) {
+    n_sel = 0;
+    s_found = 0;
+    s_last_v = INFINITY;
+    s_last_c = -1;
+  }
+  __syncthreads();
+  if (tid == 0) s_bmax = fmaxf(fmaxf(red_v[0], red_v[1]), fmaxf(red_v[2], red_v[3]));
+  __syncthreads();
+  // a. k-th best approximate score: k rounds of "best element after the previous one" in (value desc, slot asc) order
+  for (int r = 0; r < k; ++r) {
+    const float lv = s_last_v;
+    const int lc = s_last_c;
+    float bv = -INFINITY;
+    int bc = -1;
+    for (int c = tid; c < C; c += kRefineThreads) {
+      const float v = approx[c];
+      if (v == -INFINITY) continue;
+      const bool after = v < lv || (v == lv && c > lc);
+      if (after && (bc < 0 || v > bv)) {  // slots ascend within a thread, so the first maximum wins ties
+        bv = v;
+        bc = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int c2 = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (c2 >= 0 && (bc < 0 || v2 > bv || (v2 == bv && c2 < bc))) {
+        bv = v2;
+        bc = c2;
+      }
+    }
+    if (lane == 0) {
+      red_v[warp] = bv;
+      red_c[warp] = bc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float v = red_v[0];
+      int c = red_c[0];
+      for (int w = 1; w < 4; ++w)
+        if (red_c[w] >= 0 && (c < 0 || red_v[w] > v || (red_v[w] == v && red_c[w] < c))) {
+          v = red_v[w];
+          c = red_c[w];
+        }
+      if (c >= 0) {
+        s_last_v = v;
+        s_last_c = c;
+        s_found = r + 1;
+      } else {
+        s_last_v = -INFINITY;
+        s_last_c = C;
+      }
+    }
+    __syncthreads();
+    if (s_found <= r) break;  // fewer than k candidates exist
+  }
+  // b. candidates that can still reach the top k
+  const float t = (s_found == k) ? s_last_v - 2.f * eps : -INFINITY;
+  for (int c = tid; c < C; c += kRefineThreads) {
+    const float v = approx[c];
+    if (v != -INFINITY && v >= t) {
+      const int pos = atomicAdd(&n_sel, 1);
+      if (pos < kSelCap) sel_c[pos] = c;
+    }
+  }
+  __syncthreads();
+  const int total_sel = n_sel;
+  const int ns = min(total_sel, kSelCap);
+  // c. exact scores
+  {
+    float qv[16];  // P <= 512
+    const float* qr = Qn + (size_t)q * P;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) qv[i] = (lane + 32 * i < P) ? qr[lane + 32 * i] : 0.f;
+    for (int i = warp; i < ns; i += kRefineThreads / 32) {
+      const int c = sel_c[i];
+      const int s = c / KC, j = c - s * KC;
+      const int id = cand_i[((size_t)s * Q + q) * KC + j];
+      const float* dr = Dn + (size_t)id * P;
+      float dot = 0.f;
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii)
+        if (lane + 32 * ii < P) dot = fmaf(qv[ii], __ldg(dr + lane + 32 * ii), dot);
+      dot = warp_sum(dot);
+      if (lane == 0) {
+        sel_s[i] = dot;
+        sel_id[i] = id;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
   float last_s = INFINITY, kth = -INFINITY;
   long long last_i = -1;
   int found = 0;
   for (int r = 0; r < k; ++r) {
     float bs = -INFINITY;
     long long bi = -1;
-    for (int c = lane; c < C; c += 32) {
-      const int s = c / KC, j = c - s * KC;
-      const long long id = cand_i[((size_t)s * Q + q) * KC + j];
-      if (id < 0) continue;
-      const float sv = sc[c];
+    for (int i = lane; i < ns; i += 32) {
+      const float sv = sel_s[i];
+      const long long id = sel_id[i];
       const bool after = (r == 0) || better(last_s, last_i, sv, id);
       if (after && (bi < 0 || better(sv, id, bs, bi))) {
         bs = sv;
@@ -386,8 +484,11 @@ __global__ void __launch_bounds__(128)
       last_i = -1;
     }
   }
-  // a document outside the candidate lists could only matter if its exact score can reach the k-th best
-  if (lane == 0) flag[q] = ((found == k && bmax + eps >= kth) || (found < k && bmax > -INFINITY)) ? 1 : 0;
+  // d. a document outside the candidate lists could only matter if its exact score can reach the k-th best
+  if (lane == 0) {
+    const float bmax = s_bmax;
+    flag[q] = (total_sel > kSelCap || (found == k && bmax + eps >= kth) || (found < k && bmax > -INFINITY)) ? 1 : 0;
+  }
 }
 
 // ordered compaction of the flagged query rows (single CTA: Q is at most a few hundred thousand)
@@ -436,19 +537,23 @@ int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
   if (pl.pair) pl.n_qtiles = (pl.n_qtiles + 1) / 2 * 2;
   pl.KB = (P + BK - 1) / BK;
   const long long tiles = (N + TD - 1) / TD;
-  // document splits: fill the machine when there are few query tiles, otherwise aim at whole waves
+  // document splits.  One CTA per SM, so the n_qtiles x S CTAs run in strict waves of `sms`; a CTA costs its
+  // document tiles plus a fixed prologue/epilogue worth ~6 tiles, and every split adds candidate handling.  Take
+  // the S that minimises  waves(S) x (tiles / S + 6)  (+ a small handicap per split).
   int S = 1;
   const int sms = sm_count();
-  if (pl.n_qtiles < 2 * sms) {
-    S = (2 * sms + pl.n_qtiles - 1) / pl.n_qtiles;
-    if (pl.n_qtiles == 1) S = sms;
+  if (pl.n_qtiles == 1) {
+    S = sms;
   } else {
-    // smallest S <= 8 that leaves the last wave at least 85 % full
-    for (int c = 1; c <= 8; ++c) {
-      const long long ctas = (long long)pl.n_qtiles * c;
-      const double waves = (double)ctas / sms;
-      if (waves / (double)((ctas + sms - 1) / sms) >= 0.85) { S = c; break; }
-      S = c;
+    double best = 0.0;
+    const int smax = (int)(tiles / 8 < 1 ? 1 : (tiles / 8 > kMaxSplits ? kMaxSplits : tiles / 8));
+    for (int c = 1; c <= smax; ++c) {
+      const long long waves = ((long long)pl.n_qtiles * c + sms - 1) / sms;
+      const double cost = (double)waves * ((double)tiles / c + 6.0) * (1.0 + 0.004 * (c - 1));
+      if (c == 1 || cost < best) {
+        best = cost;
+        S = c;
+      }
     }
   }
   if (S > tiles) S = (int)tiles;
@@ -473,8 +578,8 @@ int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
 }
 
 int scan_pair_enabled() {
-  const char* e = getenv("TT_SCAN_PAIR");  // tuning hook: 0 forces the single-CTA kernel
-  return e ? atoi(e) : 1;
+  const char* e = getenv("TT_SCAN_PAIR");  // tuning hook: 1 selects the cta_group::2 kernel (measured slower so far)
+  return e ? atoi(e) : 0;
 }
 
 int scan_stagger() {
@@ -567,11 +672,8 @@ int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void
   }
 
   const int C = pl.S * pl.KC;
-  const long long warps = (long long)Q * ((C + kGroup - 1) / kGroup);
-  rescore_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(Qn, Dn, w.cand_i, pl.S, Q, pl.KC, P, w.exact);
-  TT_LAUNCH_CHECK();
-  select_kernel<<<(Q + 3) / 4, 128, 0, st>>>(w.exact, w.cand_i, w.bound, pl.S, Q, pl.KC, k, id_base, scan_eps(), top_score,
-                                             top_id, w.flag);
+  refine_kernel<<<Q, kRefineThreads, (size_t)C * sizeof(float), st>>>(Qn, Dn, w.cand_s, w.cand_i, w.bound, pl.S, Q, pl.KC, P,
+                                                                     k, id_base, scan_eps(), top_score, top_id, w.flag);
   TT_LAUNCH_CHECK();
   compact_flags_kernel<<<1, 1024, 0, st>>>(w.flag, Q, w.qlist, w.qcount);
   TT_LAUNCH_CHECK();

@@ -158,9 +158,8 @@ class FusedTrainer:
             self.xchg = comm.DpExchange(self.n_param, world_size, rank, dev, group=process_group)
             self.flat_p = self.xchg.flat_p
             self.side = torch.cuda.Stream(device=dev, priority=-1)
-            self.ev_back = torch.cuda.Event()
-            self.ev_xchg = torch.cuda.Event()
             self._xchg_pending = False
+            self.graph_ov = None
         else:
             self.flat_p = torch.empty(self.n_param, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(self.n_param + 1, dtype=torch.float32, device=dev)  # [+1]: loss
@@ -180,13 +179,26 @@ class FusedTrainer:
         # where the step's GLOBAL loss can be read: slot n of the flat gradient (summed in place by NCCL), or slot n
         # of the peer segment (written by the exchange kernel)
         self.loss_view = self.xchg.loss if self.xchg is not None else self.flat_g[self.n_param:]
-        # static token buffers (graph replays read these addresses)
-        mk = lambda L, dt_: torch.zeros(batch_size, L, dtype=dt_, device=dev)  # noqa: E731
-        new_set = lambda: (mk(Lq, ids_dtype), mk(Lq, mask_dtype), mk(Ld, ids_dtype), mk(Ld, mask_dtype),  # noqa: E731
-                           mk(Ld, ids_dtype), mk(Ld, mask_dtype))
+        # static token buffers (graph replays read these addresses).  The six tensors of a slot are views of ONE
+        # byte buffer so that a step's tokens arrive with a single H2D copy (load_packed)
+        self._tok_layout = []
+        off = 0
+        for L, dt_ in ((Lq, ids_dtype), (Lq, mask_dtype), (Ld, ids_dtype), (Ld, mask_dtype), (Ld, ids_dtype),
+                       (Ld, mask_dtype)):
+            nbytes = batch_size * L * torch.empty((), dtype=dt_).element_size()
+            self._tok_layout.append((off, nbytes, L, dt_))
+            off += (nbytes + 255) // 256 * 256
+        self.tok_bytes = off
+
+        def new_set():
+            buf = torch.zeros(self.tok_bytes, dtype=torch.uint8, device=dev)
+            return buf, tuple(buf[o: o + nb].view(dt_).view(batch_size, L) for o, nb, L, dt_ in self._tok_layout)
+
         # token_slots > 1: rotating input buffers (prefetch step i+1 while step i computes; each slot has
         # its own captured graph because a graph replays fixed addresses)
-        self.tok_slots = [new_set() for _ in range(max(1, token_slots))]
+        sets = [new_set() for _ in range(max(1, token_slots))]
+        self.tok_bufs = [b for b, _ in sets]
+        self.tok_slots = [v for _, v in sets]
         self.tok = self.tok_slots[0]
         self.table_grads = None
         if self.train_table:
@@ -216,28 +228,48 @@ class FusedTrainer:
         self.step_obj.run(slot, phases)
 
     def _exchange(self):
-        """Peer mode: the fused reduce-scatter / Adam / all-gather kernel on the high-priority side stream."""
-        self.ev_back.record()
-        self.side.wait_event(self.ev_back)
+        """The fused reduce-scatter / Adam / all-gather kernel (tt_dp_reduce_adam) on the current stream."""
+        self.xchg.reduce_adam(self.flat_g, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps,
+                              self.exchange_ctas)
+
+    def _overlapped(self, slot: int):
+        """{exchange of the PREVIOUS step's gradients  ||  pooled gather of this step} -> rest of this step.
+        The gather reads tokens and the frozen tables only, never the projection weights, so running it beside
+        the exchange is still exact synchronous SGD.  The exchange sits on a high-priority stream: its few CTAs
+        get SM slots first and the gather fills the rest."""
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
-            self.xchg.reduce_adam(self.flat_g, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps,
-                                  self.exchange_ctas)
-            self.ev_xchg.record()
-        self._xchg_pending = True
+            self._exchange()
+        self._fwd_bwd(slot, 1)
+        cur.wait_stream(self.side)
+        self._fwd_bwd(slot, 2)
 
     def wait(self):
-        """Makes the current stream wait for the last step's parameter exchange (peer mode runs it on a side
-        stream so that it overlaps the next step's pooled gather).  Call before reading parameters or the loss."""
+        """Peer mode keeps the last step's gradients un-exchanged until the next step (whose pooled gather hides
+        the exchange); wait() runs that pending exchange now.  Call before reading parameters or `loss_view`."""
         if self.xchg is not None and self._xchg_pending:
-            torch.cuda.current_stream().wait_event(self.ev_xchg)
+            self._exchange()
+            self._xchg_pending = False
 
     def read_loss_async(self, host_dst: torch.Tensor):
-        """Copies the last step's global loss into pinned host memory without stalling the step pipeline."""
-        if self.xchg is not None:
-            with torch.cuda.stream(self.side):
-                host_dst.copy_(self.loss_view.reshape(host_dst.shape), non_blocking=True)
-        else:
-            host_dst.copy_(self.loss_view.reshape(host_dst.shape), non_blocking=True)
+        """Copies the newest available global loss into pinned host memory without a sync.  In peer mode that is
+        the loss of the previous step (this step's loss term is still waiting for its exchange)."""
+        host_dst.copy_(self.loss_view.reshape(host_dst.shape), non_blocking=True)
+
+    def pack_host_tokens(self, tensors, pin: bool = True) -> torch.Tensor:
+        """(q_ids,q_mask,p_ids,p_mask,n_ids,n_mask) host tensors -> one (pinned) byte buffer in slot layout."""
+        buf = torch.zeros(self.tok_bytes, dtype=torch.uint8)
+        if pin:
+            buf = buf.pin_memory()
+        for (o, nb, L, dt_), t in zip(self._tok_layout, tensors):
+            assert t.dtype == dt_ and tuple(t.shape) == (self.B, L), (t.dtype, tuple(t.shape))
+            buf[o: o + nb].view(dt_).view(self.B, L).copy_(t)
+        return buf
+
+    def load_packed(self, host_buf: torch.Tensor, slot: int = 0):
+        """One H2D copy of a pack_host_tokens() buffer into the slot's static device buffers (current stream)."""
+        self.tok_bufs[slot].copy_(host_buf, non_blocking=True)
 
     def _optimizer(self):
         b1, b2 = self.betas
@@ -256,16 +288,20 @@ class FusedTrainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         lib = ops.N.load()
+        if self.xchg is not None:
+            self.graph_ov = [None] * len(self.tok_slots)
         for slot in range(len(self.tok_slots)):
             n0 = lib.tt_launch_count()
-            if self.xchg is not None:  # two graphs per slot: the exchange of the previous step overlaps the first
-                gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gf):
-                    self._fwd_bwd(slot, 1)
-                with torch.cuda.graph(gb):
-                    self._fwd_bwd(slot, 2)
-                self.graph_fb[slot] = (gf, gb)
-                self.kernel_launches_per_step = lib.tt_launch_count() - n0 + 1
+            if self.xchg is not None:  # two graphs per slot: a plain step, and one that starts with the pending exchange
+                g0, g1 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g0):
+                    self._fwd_bwd(slot)
+                n1 = lib.tt_launch_count()
+                with torch.cuda.graph(g1):
+                    self._overlapped(slot)
+                self.graph_fb[slot] = g0
+                self.graph_ov[slot] = g1
+                self.kernel_launches_per_step = lib.tt_launch_count() - n1
                 continue
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -283,24 +319,24 @@ class FusedTrainer:
 
     def step(self, slot: int = 0) -> torch.Tensor:
         """One optimiser step on the tokens currently in the static buffers of `slot`; returns the (global)
-        loss as a device scalar — no host sync."""
+        loss as a device scalar — no host sync.  Peer mode: the gradient exchange + Adam of this step runs at
+        the start of the next step() (hidden under its pooled gather) or at wait(), whichever comes first; the
+        returned scalar is valid after wait()."""
         if self.use_graph and self.graph_fb[0] is None:
             self._capture()  # warm-up runs forward/backward only, capture itself executes nothing
         if self.xchg is not None:
-            # pooled gather of THIS step (tokens + frozen tables only) may run while the previous step's exchange
-            # is still landing parameters; everything after it waits for the exchange
             lib = ops.N.load()
             n0 = lib.tt_launch_count()
-            if self.use_graph:
-                self.graph_fb[slot][0].replay()
+            if self._xchg_pending:  # steady state: previous exchange || this gather, then the rest
+                if self.use_graph:
+                    self.graph_ov[slot].replay()
+                else:
+                    self._overlapped(slot)
+            elif self.use_graph:
+                self.graph_fb[slot].replay()
             else:
-                self._fwd_bwd(slot, 1)
-            self.wait()
-            if self.use_graph:
-                self.graph_fb[slot][1].replay()
-            else:
-                self._fwd_bwd(slot, 2)
-            self._exchange()
+                self._fwd_bwd(slot)
+            self._xchg_pending = True
             if not self.use_graph:
                 self.kernel_launches_per_step = lib.tt_launch_count() - n0
         elif self.use_graph:
@@ -322,6 +358,7 @@ class FusedTrainer:
     def close(self):
         """Releases the peer segment (collective in peer mode: call on every rank after a barrier)."""
         if self.xchg is not None:
+            self.wait()
             torch.cuda.synchronize()
             self.xchg.check()
             # parameters move back to ordinary torch memory so the model outlives the segment
