@@ -14,7 +14,8 @@ every rank processes its own 2048-triplet batch; the one exchange per step is a 
 all-gather kernel over NVLink peer memory (TT_DP_EXCHANGE=nccl selects all-reduce + Adam instead).
 
 A "step" = H2D'd tokens -> pooled gather (q,p,n) -> both tower MLPs -> cosine triplet loss -> all gradients
--> [gradient exchange +] Adam.  Prints ONE JSON line on rank 0.
+-> [gradient exchange +] Adam.  Steps are software-pipelined: the pooled gather of step i+1 (tokens + frozen tables
+only) runs beside the rest of step i; every step still does all of its own work.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -225,9 +226,10 @@ def run_b200(args):
         return float(t.item())
 
     K, W = args.steps, args.warmup
+    NS = N_TOKEN_SETS
+    trainer.prepare()  # capture the round-robin step graphs up front
     for i in range(W):
-        trainer.step(i % N_TOKEN_SETS)
-    trainer.wait()
+        trainer.step(i % NS, (i + 1) % NS)
     barrier()
     launches_per_step = int(trainer.kernel_launches_per_step or 0)
 
@@ -239,8 +241,7 @@ def run_b200(args):
     t_wall0 = time.time()
     ev0.record()
     for i in range(K):
-        trainer.step((W + i) % N_TOKEN_SETS)
-    trainer.wait()  # peer mode: the last step's exchange (the others ran under the following step's gather)
+        trainer.step((W + i) % NS, (W + i + 1) % NS)  # the next step's pooled gather runs beside this step
     ev1.record()
     barrier()
     t_wall1 = time.time()
@@ -257,18 +258,22 @@ def run_b200(args):
     done = [torch.cuda.Event() for _ in range(4)]
     ready = [torch.cuda.Event() for _ in range(4)]
 
-    def e2e_step(i):
-        slot = i % N_TOKEN_SETS
-        if i >= 2:
-            copy_stream.wait_event(done[(i - 2) % 4])  # bounded prefetch; slot reuse is N_TOKEN_SETS steps away
+    def stage(j):  # tokens of step j: pinned host -> its slot, on the copy stream, at most 3 steps ahead
+        if j >= 3:
+            copy_stream.wait_event(done[(j - 3) % 4])
         with torch.cuda.stream(copy_stream):
-            trainer.load_packed(host_packed[slot], slot)
-            ready[i % 4].record(copy_stream)
-        main.wait_event(ready[i % 4])
-        trainer.step(slot)
-        trainer.read_loss_async(loss_host[i: i + 1])  # peer mode: the previous step's loss (exchange is pipelined)
+            trainer.load_packed(host_packed[j % NS], j % NS)
+            ready[j % 4].record(copy_stream)
+
+    def e2e_step(i):
+        stage(i + 1)                       # step i launches the pooled gather of step i + 1, so stage one ahead
+        main.wait_event(ready[(i + 1) % 4])
+        trainer.step(i % NS, (i + 1) % NS)
+        trainer.read_loss_async(loss_host[i: i + 1])
         done[i % 4].record(main)
 
+    stage(0)
+    main.wait_event(ready[0])
     for i in range(W):
         e2e_step(i)
     barrier()
@@ -276,8 +281,6 @@ def run_b200(args):
     ev0.record()
     for i in range(W, W + K):
         e2e_step(i)
-    trainer.wait()
-    trainer.read_loss_async(loss_host[W + K: W + K + 1])
     ev1.record()
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))

@@ -25,17 +25,18 @@ for exchange in ("nccl", "peer", "peer-pipelined"):
     torch.manual_seed(0)
     model = TwoTowersModel(projection_dim=P, vocab_size=V, precision="bf16x3").to(dev)
     tr = FusedTrainer(model, 0.3, 1e-3, B, Lq, Ld, precision="bf16x3", world_size=world, rank=rank,
-                      ids_dtype=torch.int64, mask_dtype=torch.int64, exchange=exchange.split("-")[0])
+                      ids_dtype=torch.int64, mask_dtype=torch.int64, exchange=exchange.split("-")[0], token_slots=2)
     losses = []
+    batches = [O.synth_triplet_batch(B, Lq, Ld, "U", seed=100 * i + rank, vocab=V) for i in range(STEPS)]
+    tr.load_packed(tr.pack_host_tokens(batches[0].astuple(), pin=False), 0)
     for i in range(STEPS):
-        b = O.synth_triplet_batch(B, Lq, Ld, "U", seed=100 * i + rank, vocab=V)
-        for dst, src in zip(tr.tok, b.astuple()):
-            dst.copy_(src)
-        tr.step()
-        if exchange != "peer-pipelined":
-            tr.wait()
-            losses.append(float(tr.loss_view[0].item()))
-    tr.wait()
+        nslot = None
+        if i + 1 < STEPS:
+            if exchange == "peer-pipelined":
+                nslot = (i + 1) % 2
+            tr.load_packed(tr.pack_host_tokens(batches[i + 1].astuple(), pin=False), (i + 1) % 2)
+        tr.step(i % 2, nslot)
+        losses.append(float(tr.loss_view[0].item()))
     torch.cuda.synchronize()
     p = tr.flat_p.clone()
     # replicas identical?

@@ -395,33 +395,38 @@ def test_dp_exchange_virtual_ranks_match_summed_adam(tt, world, n):
             x.close()
 
 
-@pytest.mark.parametrize("use_graph,pipelined", [(False, False), (True, False), (False, True), (True, True)])
-def test_fused_trainer_peer_exchange_equals_plain_adam(tt, use_graph, pipelined):
-    """world = 1: the exchange kernel (and, pipelined, the {exchange || pooled gather} -> rest graph that hides it
-    under the next step) must reproduce the single-graph trainer bit for bit."""
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_trainer_pipelined_and_peer_exchange_equal_plain_steps(tt, use_graph):
+    """Three ways to run the same 5 steps must agree bit for bit: (a) plain sequential steps, (b) software-pipelined
+    steps (pooled gather of step i+1 beside the rest of step i, alternating workspaces), (c) pipelined with the
+    fused peer-memory exchange kernel as the optimiser (world = 1)."""
     B, Lq, Ld, P, V = 256, 16, 64, 128, 4096
-    batches = [O.synth_triplet_batch(B, Lq, Ld, "U", seed=20 + i, vocab=V) for i in range(4)]
+    batches = [O.synth_triplet_batch(B, Lq, Ld, "U", seed=20 + i, vocab=V) for i in range(5)]
     out = []
-    for exchange in (None, "peer"):
+    for mode in ("plain", "pipelined", "pipelined+peer"):
         torch.manual_seed(4)
         m = tt.TwoTowersModel(projection_dim=P, vocab_size=V, precision="bf16x3").to(DEV)
         tr = tt.training.FusedTrainer(m, 0.3, 1e-3, B, Lq, Ld, precision="bf16x3", use_graph=use_graph,
-                                      ids_dtype=torch.int64, mask_dtype=torch.int64, exchange=exchange)
+                                      ids_dtype=torch.int64, mask_dtype=torch.int64, token_slots=2,
+                                      exchange="peer" if mode.endswith("peer") else None)
         losses = []
-        for b in batches:
-            tr.load_packed(tr.pack_host_tokens(b.astuple(), pin=False))
-            tr.step()
-            if not pipelined:
-                tr.wait()
-                losses.append(float(tr.loss_view[0].item()))
-        tr.wait()
-        losses.append(float(tr.loss_view[0].item()))
+        tr.load_packed(tr.pack_host_tokens(batches[0].astuple(), pin=False), 0)
+        for i, b in enumerate(batches):
+            slot, nslot = i % 2, None
+            if mode != "plain" and i + 1 < len(batches):
+                nslot = (i + 1) % 2
+                tr.load_packed(tr.pack_host_tokens(batches[i + 1].astuple(), pin=False), nslot)
+            tr.step(slot, nslot)
+            losses.append(float(tr.loss_view[0].item()))
+            if mode == "plain" and i + 1 < len(batches):
+                tr.load_packed(tr.pack_host_tokens(batches[i + 1].astuple(), pin=False), (i + 1) % 2)
         torch.cuda.synchronize()
         out.append((tr.flat_p.clone(), losses))
         tr.close()
         assert torch.equal(m.query_tower.projection[0].weight.reshape(-1), out[-1][0][: P * 384])
-    assert out[0][1] == out[1][1]
-    assert torch.equal(out[0][0], out[1][0])
+    for other in out[1:]:
+        assert out[0][1] == other[1]
+        assert torch.equal(out[0][0], other[0])
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -95,16 +95,21 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and issuer loops run on the whole warp, one elected lane per asynchronous instruction: in a divergent
+  // `lane == 0` region every UTMALDG / UTCHMMA / UTCBAR is wrapped in an ELECT + BRA.U.ANY loop (~80 clk each).
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer --------------------------------------------------------------------
+    {  // ---- TMA producer -------------------------------------------------------------------------------------
       int s = 0;  // ring slot and its phase, advanced incrementally (no integer division in the hot loops)
       uint32_t ph = 0;
       for (int kbi = 0; kbi < n_kb; ++kbi) {
         for (int j = 0; j < T; ++j) {
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          tma_load_2d(smem + s * kStageBytes, &g.a[j], &full[s], (kb0 + kbi) * BK, m0);
-          tma_load_2d(smem + s * kStageBytes + kABytes, &g.b[j], &full[s], (kb0 + kbi) * BK, n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[s], kStageBytes);
+            tma_load_2d(smem + s * kStageBytes, &g.a[j], &full[s], (kb0 + kbi) * BK, m0);
+            tma_load_2d(smem + s * kStageBytes + kABytes, &g.b[j], &full[s], (kb0 + kbi) * BK, n0);
+          }
+          __syncwarp();
           if (++s == NS) {
             s = 0;
             ph ^= 1u;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer ------------------------------------------------------------------------
+    {  // ---- MMA issuer ---------------------------------------------------------------------------------------
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       const uint32_t ring = smem_u32(smem);
       int s = 0;
@@ -131,16 +136,19 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
           }
         }
         tc_fence_after();
-        for (int pair = 0; pair < p.n_pairs; ++pair) {
-          const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
-          const uint64_t da = make_smem_desc_sw128(slot_addr[ai]), db = make_smem_desc_sw128(slot_addr[bi] + kABytes);
+        if (elect_one()) {
+          for (int pair = 0; pair < p.n_pairs; ++pair) {
+            const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
+            const uint64_t da = make_smem_desc_sw128(slot_addr[ai]), db = make_smem_desc_sw128(slot_addr[bi] + kABytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
-            mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kbi | pair | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
+              mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kbi | pair | k) != 0);
+          }
+          for (int j = 0; j < T; ++j) mma_commit(&empty[slot_id[j]]);  // frees the slots once these MMAs have read them
+          if (kbi == n_kb - 1) mma_commit(tmem_full);
         }
-        for (int j = 0; j < T; ++j) mma_commit(&empty[slot_id[j]]);  // frees the slots once these MMAs have read them
+        __syncwarp();
       }
-      mma_commit(tmem_full);
     }
   } else {  // ---- epilogue: warp quarter q owns TMEM lanes [32q, 32q+32) -----------------------------------
     mbar_wait(tmem_full, 0);
@@ -597,7 +605,7 @@ struct StepWs {
   bf16 *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;    // [3B,P], [P,ldt]
   bf16 *w1_hi[2], *w1_lo[2], *w1_lo2[2], *w1t_hi[2], *w1t_lo[2];  // per tower: [P,H], [H,P]
   bf16 *w2_hi[2], *w2_lo[2], *w2t_hi[2], *w2t_lo[2];  // per tower: [P,P], [P,P]
-  float *dz1, *partial, *colsum, *loss_scratch;
+  float *dz1, *partial, *partial2, *colsum, *colsum2, *loss_scratch;
 };
 
 size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out) {
@@ -623,7 +631,9 @@ size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out)
   }
   w.dz1 = ws_take<float>(p, R * P);
   w.partial = ws_take<float>(p, (size_t)2 * 32 * P * max(P, H));
+  w.partial2 = ws_take<float>(p, (size_t)2 * 32 * P * P);  // dW2's split-K sums: it runs beside the dW1 branch
   w.colsum = ws_take<float>(p, (size_t)2 * kColsumSlices * P);
+  w.colsum2 = ws_take<float>(p, (size_t)2 * kColsumSlices * P);
   w.loss_scratch = ws_take<float>(p, (size_t)(B + 3) / 4 + 8);
   (void)train_table;
   if (out) *out = w;
@@ -633,6 +643,31 @@ size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out)
 }  // namespace
 
 size_t step_sm100_ws_bytes(int B, int H, int P, int train_table) { return carve_step(nullptr, B, H, P, train_table, nullptr); }
+
+// Auxiliary streams + events for the independent branches of the backward chain.  Created on first use (the first
+// call is never inside a stream capture: FusedTrainer warms up eagerly); fork()/join() are capture-legal, so in a
+// CUDA graph the branches become parallel paths of the DAG.
+struct Forks {
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int device = -1;
+};
+static int get_forks(Forks** out) {
+  static thread_local Forks f;
+  int dev = 0;
+  TT_CUDA(cudaGetDevice(&dev));
+  if (f.device != dev) {
+    for (auto& a : f.aux) TT_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    for (auto& e : f.ev) TT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    f.device = dev;
+  }
+  *out = &f;
+  return 0;
+}
+static int step_concurrency() {
+  const char* e = getenv("TT_STEP_FORK");  // tuning hook: 0 = one serial chain
+  return e ? atoi(e) : 1;
+}
 
 int step_sm100(const StepSm100& s, cudaStream_t st) {
   const int B = s.B, H = s.H, P = s.P, np = s.n_split;
@@ -700,9 +735,18 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
   if ((rc = triplet_loss_fused(yq, yp, yn, B, P, s.margin, s.inv_batch, s.grad_scale, s.stats, s.loss, s.dy,
                                s.dy + (size_t)B * P, s.dy + (size_t)2 * B * P, &so, w.loss_scratch, st)))
     return rc;
-  if ((rc = transpose_pair(w.dy_hi, w.dy_lo, 3 * B, P, w.dyt_hi, w.dyt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
-  // 6. db2, dW2 = dY^T h   (split-K over the batch rows)
-  if ((rc = colsum2(s.dy, rows[0], db2[0], s.dy + (size_t)row0[1] * P, rows[1], db2[1], P, P, 0, w.colsum, st))) return rc;
+  // From here the chain forks: {dY^T -> dW2}, {db2, db1} and {dz1 -> dW1} only share inputs.
+  Forks* fk = nullptr;
+  if ((rc = get_forks(&fk))) return rc;
+  const bool fork = step_concurrency() != 0;
+  cudaStream_t sA = fork ? fk->aux[0] : st, sB = fork ? fk->aux[1] : st;
+  if (fork) {
+    TT_CUDA(cudaEventRecord(fk->ev[0], st));
+    TT_CUDA(cudaStreamWaitEvent(sA, fk->ev[0], 0));
+    TT_CUDA(cudaStreamWaitEvent(sB, fk->ev[0], 0));
+  }
+  // 6a. (branch A) dY^T, then dW2 = dY^T h   (split-K over the batch rows)
+  if ((rc = transpose_pair(w.dy_hi, w.dy_lo, 3 * B, P, w.dyt_hi, w.dyt_lo, w.ldt, 0, B, w.dcol - B, sA))) return rc;
   for (int t = 0; t < 2; ++t) {
     g[t] = GemmDesc{};
     g[t].A = {w.dyt_hi + tcol[t], w.dyt_lo + tcol[t], w.ldt};
@@ -710,8 +754,10 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
     g[t].M = P; g[t].N = P; g[t].K = rows[t]; g[t].C = dW2[t];
   }
   const int tiles2 = 2 * ((P + BM - 1) / BM) * ((P + BN - 1) / BN);
-  if ((rc = launch_gemm(g, 2, np, choose_splits(tiles2, B), w.partial, 0, st))) return rc;
-  // 7. dz1 = (dY W2) * (h > 0)
+  if ((rc = launch_gemm(g, 2, np, choose_splits(tiles2, B), fork ? w.partial2 : w.partial, 0, sA))) return rc;
+  // 6b. (branch B) db2
+  if ((rc = colsum2(s.dy, rows[0], db2[0], s.dy + (size_t)row0[1] * P, rows[1], db2[1], P, P, 0, w.colsum2, sB))) return rc;
+  // 7. (main) dz1 = (dY W2) * (h > 0)
   for (int t = 0; t < 2; ++t) {
     g[t] = GemmDesc{};
     g[t].A = {w.dy_hi + (size_t)row0[t] * P, w.dy_lo + (size_t)row0[t] * P, P};
@@ -724,9 +770,13 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
     g[t].Ct_hi = w.dzt_hi + tcol[t]; g[t].Ct_lo = w.dzt_lo + tcol[t]; g[t].ldt = w.ldt;
   }
   if ((rc = launch_gemm(g, 2, np, 1, nullptr, 0, st))) return rc;
-  if ((rc = colsum2(w.dz1, rows[0], db1[0], w.dz1 + (size_t)row0[1] * P, rows[1], db1[1], P, P, 0, w.colsum, st)))
+  if (fork) {  // branch B continues with db1 once dz1 exists
+    TT_CUDA(cudaEventRecord(fk->ev[1], st));
+    TT_CUDA(cudaStreamWaitEvent(sB, fk->ev[1], 0));
+  }
+  if ((rc = colsum2(w.dz1, rows[0], db1[0], w.dz1 + (size_t)row0[1] * P, rows[1], db1[1], P, P, 0, w.colsum, sB)))
     return rc;
-  // 8. dW1 = dz1^T x
+  // 8. (main) dW1 = dz1^T x
   for (int t = 0; t < 2; ++t) {
     g[t] = GemmDesc{};
     g[t].A = {w.dzt_hi + tcol[t], w.dzt_lo + tcol[t], w.ldt};
@@ -735,6 +785,12 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
   }
   const int tiles1 = 2 * ((P + BM - 1) / BM) * ((H + BN - 1) / BN);
   if ((rc = launch_gemm(g, 2, np, choose_splits(tiles1, B), w.partial, 0, st))) return rc;
+  if (fork) {  // join
+    TT_CUDA(cudaEventRecord(fk->ev[2], sA));
+    TT_CUDA(cudaEventRecord(fk->ev[3], sB));
+    TT_CUDA(cudaStreamWaitEvent(st, fk->ev[2], 0));
+    TT_CUDA(cudaStreamWaitEvent(st, fk->ev[3], 0));
+  }
   // 9. dxhat = dz1 W1 (only when the token tables train)
   if (s.dxhat) {
     for (int t = 0; t < 2; ++t) {
