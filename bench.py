@@ -201,7 +201,9 @@ def run_b200(args):
     table_dtype = torch.bfloat16 if args.table_dtype == "bf16" else torch.float32
     torch.manual_seed(0)
     model = TwoTowersModel(projection_dim=P_DIM, table_dtype=table_dtype, precision=args.precision).to(dev)
-    ids_dtype, mask_dtype = torch.int32, torch.uint8
+    # token ids travel as uint16 (vocab 30522 < 65536) and masks as uint8: 3 bytes per token over PCIe instead of the
+    # 16 bytes of the reference tokenizer's int64 ids + int64 mask (--ids-dtype i32 for 4-byte ids)
+    ids_dtype, mask_dtype = (torch.uint16 if args.ids_dtype == "u16" else torch.int32), torch.uint8
     trainer = FusedTrainer(model, MARGIN, LR, B_PER_GPU, LQ, LD, precision=args.precision, world_size=world, rank=rank,
                            use_graph=not args.no_graph, ids_dtype=ids_dtype, mask_dtype=mask_dtype,
                            token_slots=N_TOKEN_SETS)
@@ -234,10 +236,12 @@ def run_b200(args):
     launches_per_step = int(trainer.kernel_launches_per_step or 0)
 
     # ---- leg 1: device-resident inputs -----------------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("TT_BENCH_NO_SAMPLER") else None  # (diagnostic switch)
     time.sleep(0.15 if sampler else 0.0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if trainer.xchg is not None:
+        trainer.xchg.reset_timing()
     t_wall0 = time.time()
     ev0.record()
     for i in range(K):
@@ -245,6 +249,18 @@ def run_b200(args):
     ev1.record()
     barrier()
     t_wall1 = time.time()
+    exchange_us = None
+    if trainer.xchg is not None:
+        t_wait, t_rest, n_calls, t_push = trainer.xchg.timing()
+        exchange_us = {"own_push": round(t_push, 2), "wait_for_all_ranks_gradients": round(t_wait, 2),
+                       "reduce_adam_allgather": round(t_rest, 2), "calls": n_calls,
+                       "note": "inside tt_dp_reduce_adam (CTA 0 of rank 0) over the timed steps: time until every "
+                               "rank's gradient slice has landed (own push + rank skew), then sum + Adam + parameter "
+                               "broadcast; wait_per_rank: the rank that waits least arrives last"}
+        if world > 1:
+            waits = [None] * world
+            dist.all_gather_object(waits, round(t_wait, 1))
+            exchange_us["wait_per_rank"] = waits
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     loss_after = float(trainer.loss_view[0].item())
@@ -289,7 +305,8 @@ def run_b200(args):
     # ---- roofline of the dominant kernel: the pooled gather, timed alone on the launching stream -----
     esz = 2 if table_dtype == torch.bfloat16 else 4
     tok_per_triplet = LQ + 2 * LD
-    alg_bytes_per_triplet = tok_per_triplet * HIDDEN * esz + tok_per_triplet * (4 + 1) + 3 * (HIDDEN * 4 + 8)
+    ids_bytes = 2 if ids_dtype == torch.uint16 else 4
+    alg_bytes_per_triplet = tok_per_triplet * HIDDEN * esz + tok_per_triplet * (ids_bytes + 1) + 3 * (HIDDEN * 4 + 8)
     segs = (_native.PoolSeg * 3)()
     xhat = torch.empty(3 * B_PER_GPU, HIDDEN, dtype=torch.float32, device=dev)
     cnt = torch.empty(3 * B_PER_GPU, dtype=torch.float32, device=dev)
@@ -350,7 +367,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else f"f32 ({args.precision} tensor-core projection)",
-            "data": "synthetic", "config": workload_config(world, args.precision, args.table_dtype) | {"dp_exchange": exchange_kind},
+            "data": "synthetic", "config": workload_config(world, args.precision, args.table_dtype) | {"dp_exchange": exchange_kind, "token_dtypes": f"ids {args.ids_dtype}, mask u8"},
+            "dp_exchange_us": exchange_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": launches_per_step * K, "gpu_launches_per_step": launches_per_step,
@@ -491,6 +509,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TT_BENCH_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--table-dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--ids-dtype", default="u16", choices=["u16", "i32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)

@@ -247,8 +247,9 @@ size_t tt_dp_segment_bytes(size_t n_param, int world);
  * segment.  Sums run in rank order, so all ranks hold bit-identical parameters and a run is bit-reproducible.
  *   segments[world]: every rank's segment as mapped in THIS process (own entry = the local pointer);
  *   grad [n_param+1] local; exp_avg / exp_avg_sq [n_param] local (only this rank's slice is touched);
- *   state: 4 doubles {t, beta1^t, beta2^t, -}; ctl: 4 u32 {epoch, ticket, ticket, error}, both zero-initialised,
- *   local.  ctl[3] != 0 after a call means a peer did not answer within 4 s.
+ *   state: 4 doubles {t, beta1^t, beta2^t, -}; ctl: 16 u32 {epoch, ticket, ticket, error, then four u64
+ *   diagnostics: ns until all gradient flags, ns from there to kernel end, calls, ns of the own push}, both
+ *   zero-initialised, local.  ctl[3] != 0 after a call means a peer did not answer within 4 s.
  *   max_ctas: upper bound on the CTAs used (<= SM count; 0 = default 64) — every CTA spins on peer flags, so
  *   the grid must be co-resident with whatever else runs concurrently. */
 int tt_dp_reduce_adam(void* const* segments, int world, int rank, size_t n_param, const float* grad,

@@ -679,3 +679,41 @@ def test_c_abi_reports_errors_instead_of_crashing(tt):
     assert rc != 0 and "L=600" in N.last_error()
     with pytest.raises(N.NativeError):
         tt.ops.pool(torch.zeros(4, 384), torch.zeros(1, 1, dtype=torch.int64), None)  # CPU tensor: no fallback
+
+
+# ---------------------------------------------------------------------------------------------------
+# document index + search (backend/search.py surface over the scan kernel)
+# ---------------------------------------------------------------------------------------------------
+def test_document_search_engine_matches_cosine_ranking_and_persists(tt, tmp_path):
+    from two_towers_overlords_b200 import search
+
+    torch.manual_seed(0)
+    model = tt.TwoTowersModel(projection_dim=64, precision="fp32")
+    docs = [f"passage {i} mentions item {i % 17} beside thing {(i * 7) % 23} and note {(i * i) % 31}" for i in range(700)]
+    eng = search.DocumentSearchEngine(model=model, index_dir=str(tmp_path))
+    assert eng.get_index_info()["num_docs"] == 0
+    eng.ingest_documents(docs[:300], batch_size=128, clear_existing=True)
+    eng.ingest_documents(docs[300:], batch_size=256, persist=True)
+    info = eng.get_index_info()
+    assert info["num_docs"] == 700 and info["index_name"] == search.DEFAULT_INDEX_NAME
+    query = "which passage mentions item 5 beside thing 7"
+    res = eng.search(query, top_k=10)
+    assert len(res) == 10 and set(res[0]) == {"id", "content", "score", "distance"}
+    with torch.no_grad():
+        q = model.encode_queries([query]).double().cpu()
+        D = torch.cat([model.encode_documents(docs[i: i + 256]) for i in range(0, 700, 256)]).double().cpu()
+    cos = torch.nn.functional.cosine_similarity(q, D).numpy()
+    order = np.lexsort((np.arange(700), -cos))
+    for r, hit in enumerate(res):
+        assert abs(hit["score"] - (1.0 + cos[order[r]]) / 2.0) < 1e-5 and abs(hit["distance"] - (1.0 - hit["score"])) < 1e-12
+        gap_prev = cos[order[r - 1]] - cos[order[r]] if r else np.inf
+        gap_next = cos[order[r]] - cos[order[r + 1]]
+        if gap_prev > 1e-5 and gap_next > 1e-5:
+            assert hit["id"] == str(order[r]) and hit["content"] == docs[order[r]]
+    # deeper than the tensor-core list limit -> fp32 scan, same head
+    deep = eng.search(query, top_k=40)
+    assert len(deep) == 40 and [h["id"] for h in deep[:10]] == [h["id"] for h in res]
+    # the index survives the process like the reference's Redis index: a new engine finds it on disk
+    eng2 = search.DocumentSearchEngine(model=model, index_dir=str(tmp_path))
+    assert eng2.get_index_info()["num_docs"] == 700
+    assert [h["id"] for h in eng2.search(query, top_k=10)] == [h["id"] for h in res]

@@ -217,3 +217,24 @@ def test_world_size_2_plumbing_over_gloo(pkg, tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_search_model_discovery_follows_reference_rules(pkg, tmp_path):
+    """find_best_model / get_projection_dim_from_model (backend/search.py:41-117): most epochs wins, weights.pt
+    overrides, projection dim comes from query_tower.projection.2.weight."""
+    import torch
+
+    from two_towers_overlords_b200 import search
+
+    assert search.find_best_model(str(tmp_path / "missing")) is None
+    assert search.find_best_model(str(tmp_path)) is None
+    for name, P in (("e3.lr3.d64.m3.pt", 64), ("e15.lr4.d384.m3.pt", 384), ("notes.txt", 0)):
+        if P:
+            torch.save({"query_tower.projection.2.weight": torch.zeros(P, P)}, tmp_path / name)
+        else:
+            (tmp_path / name).write_text("x")
+    path, fname = search.find_best_model(str(tmp_path))
+    assert fname == "e15.lr4.d384.m3.pt" and search.get_projection_dim_from_model(path) == 384
+    torch.save({"other": torch.zeros(1)}, tmp_path / "weights.pt")
+    path, fname = search.find_best_model(str(tmp_path))
+    assert fname == "weights.pt" and search.get_projection_dim_from_model(path) == search.DEFAULT_PROJ_DIM

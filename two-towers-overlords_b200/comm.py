@@ -102,7 +102,7 @@ class DpExchange:
         self.flat_p = self.own.tensor(0, (self.n,), torch.float32)
         self.loss = self.own.tensor(self.n * 4, (1,), torch.float32)
         self.state = torch.zeros(4, dtype=torch.float64, device=self.device)
-        self.ctl = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.ctl = torch.zeros(16, dtype=torch.int32, device=self.device)
 
     @classmethod
     def virtual_ranks(cls, n_param: int, world: int, device) -> List["DpExchange"]:
@@ -128,6 +128,15 @@ class DpExchange:
         """Host sync: raises if a peer failed to answer inside the kernel's timeout."""
         if int(self.ctl[3].item()) != 0:
             raise N.NativeError("peer exchange timed out waiting for another rank")
+
+    def reset_timing(self):
+        self.ctl[4:].zero_()
+
+    def timing(self):
+        """(mean us until all ranks' gradient slices landed, mean us from there to kernel end, calls, mean us of the own push) — CTA 0's view."""
+        d = self.ctl[4:12].view(torch.int64).tolist()
+        n = max(1, d[2])
+        return d[0] / n / 1e3, d[1] / n / 1e3, d[2], d[3] / n / 1e3
 
     def close(self):
         self.own.close()

@@ -51,7 +51,8 @@ struct DpParams {
   float* v;
   float lr, beta1, beta2, eps;
   double* state;      // {t, beta1^t, beta2^t, -}
-  unsigned* ctl;      // {epoch, ticket1, ticket2, error}
+  unsigned* ctl;      // {epoch, ticket1, ticket2, error, then 4 x u64 diagnostics: ns until all gradient flags,
+                      //  ns from there to the end of the kernel, calls, ns of the own push}
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_
   unsigned* my_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p.seg[me]) + L.flag_off);
   __shared__ int s_last, s_fail;
   if (tid == 0) s_fail = 0;
+  const unsigned long long t_start = (blockIdx.x == 0 && tid == 0) ? globaltimer() : 0ull;
+  unsigned long long t_flags = 0ull;
 
   const size_t S4 = L.S / 4;
   const size_t gstride = (size_t)gridDim.x * kDpThreads;
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_
   }
   __threadfence_system();
   __syncthreads();
+  const unsigned long long t_pushed = (blockIdx.x == 0 && tid == 0) ? globaltimer() : 0ull;
   if (tid == 0) {
     const unsigned prev = atomicAdd(&p.ctl[1], 1u);
     if (prev == gridDim.x - 1) {  // every CTA of this rank has pushed: tell the owners
@@ -130,6 +134,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_
   // ---- phase 2: reduce my slice in rank order, Adam, broadcast the new parameters ----------------------------------
   if (tid < W && !wait_flag(my_flags + tid, epoch)) s_fail = 1;
   __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) t_flags = globaltimer();
   if (s_fail) {
     if (tid == 0) p.ctl[3] = 1;
     return;
@@ -186,6 +191,13 @@ __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_
   __syncthreads();
   // ---- phase 3: the last CTA holds the kernel open until every rank's parameter slice has landed here ----------------
   if (s_last && tid < W && !wait_flag(my_flags + W + tid, epoch)) p.ctl[3] = 1;
+  if (blockIdx.x == 0 && tid == 0) {  // diagnostics (CTA 0's view; it is not necessarily the last CTA)
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(p.ctl + 4);
+    d[0] += t_flags - t_start;
+    d[1] += globaltimer() - t_flags;
+    d[2] += 1ull;
+    d[3] += t_pushed - t_start;
+  }
 }
 
 // one-CTA barrier across the ranks: flags[r] points at rank r's flag array ([world] slots, slot = source rank)
