@@ -429,6 +429,55 @@ def test_fused_trainer_pipelined_and_peer_exchange_equal_plain_steps(tt, use_gra
         assert torch.equal(out[0][0], other[0])
 
 
+@pytest.mark.parametrize("exchange", [None, "peer"])
+def test_fused_trainer_checkpoint_resume_is_bit_exact(tt, tmp_path, exchange):
+    """3 steps + save + fresh trainer + load + 2 steps == 5 uninterrupted steps (weights, Adam moments, step count)."""
+    B, Lq, Ld, P, V = 128, 16, 48, 64, 2048
+    batches = [O.synth_triplet_batch(B, Lq, Ld, "Z", seed=40 + i, vocab=V) for i in range(5)]
+    Lq_, Ld_ = max(b.q_ids.shape[1] for b in batches), max(b.p_ids.shape[1] for b in batches)
+
+    def pad(t, L):
+        return torch.nn.functional.pad(t, (0, L - t.shape[1]))
+
+    def feed(tr, b):
+        toks = b.astuple()
+        toks = tuple(pad(t, Lq_ if i < 2 else Ld_) for i, t in enumerate(toks))
+        tr.load_packed(tr.pack_host_tokens(toks, pin=False))
+        tr.step()
+
+    def make():
+        torch.manual_seed(9)
+        m = tt.TwoTowersModel(projection_dim=P, vocab_size=V, precision="bf16x3").to(DEV)
+        return m, tt.training.FusedTrainer(m, 0.3, 1e-3, B, Lq_, Ld_, precision="bf16x3", ids_dtype=torch.int64,
+                                           mask_dtype=torch.int64, exchange=exchange)
+    m1, t1 = make()
+    for b in batches:
+        feed(t1, b)
+    torch.cuda.synchronize()
+    want = t1.flat_p.clone()
+    t1.close()
+    m2, t2 = make()
+    for b in batches[:3]:
+        feed(t2, b)
+    ck = str(tmp_path / "e3.lr3.d64.m3.ckpt")
+    t2.save_checkpoint(ck)
+    t2.close()
+    torch.manual_seed(123)  # different init: everything must come from the checkpoint
+    m3 = tt.TwoTowersModel(projection_dim=P, vocab_size=V, precision="bf16x3").to(DEV)
+    t3 = tt.training.FusedTrainer(m3, 0.3, 1e-3, B, Lq_, Ld_, precision="bf16x3", ids_dtype=torch.int64,
+                                  mask_dtype=torch.int64, exchange=exchange)
+    t3.load_checkpoint(ck)
+    assert t3.steps_done == 3
+    for b in batches[3:]:
+        feed(t3, b)
+    torch.cuda.synchronize()
+    assert torch.equal(t3.flat_p, want)
+    t3.close()
+    # the model part alone is what the reference's main.py saves and search.py loads
+    sd = torch.load(ck, weights_only=False)["model"]
+    assert "query_tower.projection.2.weight" in sd and tuple(sd["query_tower.projection.2.weight"].shape) == (P, P)
+
+
 # ---------------------------------------------------------------------------------------------------
 # retrieval
 # ---------------------------------------------------------------------------------------------------

@@ -80,6 +80,8 @@ __device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch) 
 }
 
 __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_constant__ DpParams p) {
+  pdl_wait();
+  pdl_launch();
   const DpLayout L = dp_layout(p.n, p.world);
   const int tid = threadIdx.x, W = p.world, me = p.rank;
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&p.ctl[0]) + 1u;
@@ -319,8 +321,8 @@ extern "C" int tt_dp_reduce_adam(void* const* segments, int world, int rank, siz
   const int cap = max_ctas > 0 ? (max_ctas < sm_count() ? max_ctas : sm_count()) : 64;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
-  dp_rs_adam_ag_kernel<<<(unsigned)ctas, kDpThreads, 0, as_stream(stream)>>>(p);
-  TT_LAUNCH_CHECK();
+  TT_CUDA(launch_pdl(dp_rs_adam_ag_kernel, dim3((unsigned)ctas), dim3(kDpThreads), 0, as_stream(stream), p));
+  note_launch();
   return 0;
 }
 

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();    // everything above overlapped the tail of the previous kernel; operands are read from here on
+  pdl_launch();
 
   // Producer and issuer loops run on the whole warp, one elected lane per asynchronous instruction: in a divergent
   // `lane == 0` region every UTMALDG / UTCHMMA / UTCBAR is wrapped in an ELECT + BRA.U.ANY loop (~80 clk each).
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             size_t n0, const float* __restrict__ partial1,
                                                             float* __restrict__ out1, size_t n1, int splits,
                                                             int accumulate) {
+  pdl_wait();
+  pdl_launch();
   const float* partial = blockIdx.y ? partial1 : partial0;
   float* out = blockIdx.y ? out1 : out0;
   const size_t n = blockIdx.y ? n1 : n0;
@@ -256,6 +260,8 @@ struct SplitJobs {
 
 __global__ void __launch_bounds__(256) split_transpose_kernel(const SplitJobs jobs) {
   __shared__ bf16 s_hi[32][33], s_lo[32][33];
+  pdl_wait();
+  pdl_launch();
   const SplitJob& J = jobs.j[blockIdx.z];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -295,6 +301,8 @@ __global__ void __launch_bounds__(256) transpose_pair_kernel(const bf16* __restr
                                                              bf16* __restrict__ tlo, int ldt, int tcol0, int split_row,
                                                              int shift) {
   __shared__ bf16 s[2][32][33];
+  pdl_wait();
+  pdl_launch();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
 #pragma unroll
@@ -424,8 +432,8 @@ int launch_gemm(const GemmDesc* d, int ngroups, int n_pairs, int splits, float* 
   }
   p.stages = gemm_stages(n_pairs);
   dim3 grid(tiles_n, tiles_m, ngroups * splits);
-  gemm_tn_kernel<<<grid, kGemmThreads, gemm_smem(p.stages), st>>>(p);
-  TT_LAUNCH_CHECK();
+  TT_CUDA(launch_pdl(gemm_tn_kernel, grid, dim3(kGemmThreads), gemm_smem(p.stages), st, p));
+  note_launch();
   if (use_partial) {
     size_t n[2] = {0, 0};
     for (int i = 0; i < ngroups; ++i) {
@@ -433,10 +441,10 @@ int launch_gemm(const GemmDesc* d, int ngroups, int n_pairs, int splits, float* 
       TT_REQUIRE(d[i].ldc == 0 || d[i].ldc == d[i].N, "gemm: split-K output must be dense");
     }
     const size_t nmax = n[0] > n[1] ? n[0] : n[1];
-    splitk_reduce_kernel<<<dim3((unsigned)((nmax / 4 + 255) / 256), ngroups), 256, 0, st>>>(
-        p.g[0].partial, d[0].C, n[0], ngroups > 1 ? p.g[1].partial : nullptr, ngroups > 1 ? d[1].C : nullptr, n[1],
-        splits, accumulate);
-    TT_LAUNCH_CHECK();
+    TT_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)((nmax / 4 + 255) / 256), ngroups), dim3(256), 0, st,
+                       (const float*)p.g[0].partial, d[0].C, n[0], (const float*)(ngroups > 1 ? p.g[1].partial : nullptr),
+                       ngroups > 1 ? d[1].C : (float*)nullptr, n[1], splits, accumulate));
+    note_launch();
   } else {
     TT_REQUIRE(!accumulate, "gemm: accumulate needs the split-K path");  // checked before the launch in practice
   }
@@ -459,8 +467,8 @@ int split_jobs(const SplitJob* jobs, int n, cudaStream_t st) {
     rmax = max(rmax, jobs[i].R);
     cmax = max(cmax, jobs[i].C);
   }
-  split_transpose_kernel<<<dim3((cmax + 31) / 32, (rmax + 31) / 32, n), 256, 0, st>>>(J);
-  TT_LAUNCH_CHECK();
+  TT_CUDA(launch_pdl(split_transpose_kernel, dim3((cmax + 31) / 32, (rmax + 31) / 32, n), dim3(256), 0, st, J));
+  note_launch();
   return 0;
 }
 
@@ -473,8 +481,8 @@ int split_transpose(const float* X, int R, int C, long long ld, bf16* hi, bf16* 
 int transpose_pair(const bf16* hi, const bf16* lo, int R, int C, bf16* thi, bf16* tlo, int ldt, int tcol0,
                    int split_row, int shift, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (R + 31) / 32);
-  transpose_pair_kernel<<<grid, 256, 0, st>>>(hi, lo, R, C, thi, tlo, ldt, tcol0, split_row, shift);
-  TT_LAUNCH_CHECK();
+  TT_CUDA(launch_pdl(transpose_pair_kernel, grid, dim3(256), 0, st, hi, lo, R, C, thi, tlo, ldt, tcol0, split_row, shift));
+  note_launch();
   return 0;
 }
 

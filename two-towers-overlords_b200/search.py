@@ -185,8 +185,15 @@ class DocumentSearchEngine:
         out: list[list[dict[str, Any]]] = []
         if k <= 32:
             s, i = self.shard.search(q, k)
-        else:  # the tensor-core scan keeps at most 32 results per query; deeper lists take the fp32 scan
-            s, i = ops.scan_topk(ops.l2_normalize_rows(q), self.shard.Dn, k=k, precision="fp32")
+        else:  # the scan keeps at most 32 results per query; deeper lists score every document exactly, then sort
+            Qn = ops.l2_normalize_rows(q)
+            n = len(self.documents)
+            s = torch.empty(len(queries), k, dtype=torch.float32, device=self.device)
+            i = torch.empty(len(queries), k, dtype=torch.int64, device=self.device)
+            for qi in range(len(queries)):
+                sc = torch.from_numpy(ops.candidate_scores(Qn[qi: qi + 1], self.shard.Dn, np.arange(n))).to(self.device)
+                order = torch.sort(sc, descending=True, stable=True).indices[:k]  # stable: ties by ascending id
+                s[qi], i[qi] = sc[order], order
         scores_all, ids_all = s.cpu().numpy(), i.cpu().numpy()
         for qi in range(len(queries)):
             rows = []

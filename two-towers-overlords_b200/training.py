@@ -360,6 +360,47 @@ class FusedTrainer:
         self.steps_done += 1
         return self.loss_view[0]
 
+    # -- checkpoint / resume (main.py:142-152 saves `model.state_dict()`; this adds the optimiser so a run can resume) --
+    def _slice_bounds(self):
+        per = (self.n_param + 1 + self.world - 1) // self.world
+        S = (per + 63) // 64 * 64
+        return min(self.rank * S, self.n_param), min((self.rank + 1) * S, self.n_param)
+
+    def state_dict(self) -> dict:
+        """Model weights (reference key names) + Adam moments and step count.  Collective in peer mode with
+        world_size > 1 (the moments are sharded over the ranks there)."""
+        m, v = self.exp_avg.clone(), self.exp_avg_sq.clone()
+        if self.xchg is not None and self.world > 1:
+            torch.distributed.all_reduce(m, group=self.pg)   # every rank holds zeros outside its own slice
+            torch.distributed.all_reduce(v, group=self.pg)
+        st = self.xchg.state if self.xchg is not None else self.adam_state
+        return {"model": {k: t.detach().cpu().clone() for k, t in self.model.state_dict().items()},
+                "exp_avg": m.cpu(), "exp_avg_sq": v.cpu(), "adam_state": st.detach().cpu().clone(),
+                "steps_done": self.steps_done, "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps}
+
+    def load_state_dict(self, sd: dict):
+        self.model.load_state_dict(sd["model"])  # in-place copies: the parameters keep aliasing the flat buffer
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        if self.xchg is not None:
+            lo, hi = self._slice_bounds()
+            for t in (self.exp_avg, self.exp_avg_sq):  # keep the "zeros outside my slice" invariant
+                t[:lo].zero_()
+                t[hi:].zero_()
+            self.xchg.state.copy_(sd["adam_state"])
+        else:
+            self.adam_state.copy_(sd["adam_state"])
+        self.steps_done = int(sd.get("steps_done", 0))
+        self._primed = None
+
+    def save_checkpoint(self, path: str):
+        sd = self.state_dict()
+        if self.rank == 0:
+            torch.save(sd, path)
+
+    def load_checkpoint(self, path: str):
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+
     def close(self):
         """Releases the peer segment (collective in peer mode: call on every rank after a barrier)."""
         if self.xchg is not None:
