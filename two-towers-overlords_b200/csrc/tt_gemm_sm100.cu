@@ -97,21 +97,18 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
   pdl_wait();    // everything above overlapped the tail of the previous kernel; operands are read from here on
   pdl_launch();
 
-  // Producer and issuer loops run on the whole warp, one elected lane per asynchronous instruction: in a divergent
-  // `lane == 0` region every UTMALDG / UTCHMMA / UTCBAR is wrapped in an ELECT + BRA.U.ANY loop (~80 clk each).
+  // Producer and issuer loops run on one lane chosen by elect.sync: in a `lane == 0` region every UTMALDG / UTCHMMA /
+  // UTCBAR is wrapped in an ELECT + BRA.U.ANY loop (~80 clk each); under an elect.sync predicate they issue directly.
   if (warp == 0) {
-    {  // ---- TMA producer -------------------------------------------------------------------------------------
+    if (elect_one()) {  // ---- TMA producer ------------------------------------------------------------------------
       int s = 0;  // ring slot and its phase, advanced incrementally (no integer division in the hot loops)
       uint32_t ph = 0;
       for (int kbi = 0; kbi < n_kb; ++kbi) {
         for (int j = 0; j < T; ++j) {
           mbar_wait(&empty[s], ph ^ 1u);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&full[s], kStageBytes);
-            tma_load_2d(smem + s * kStageBytes, &g.a[j], &full[s], (kb0 + kbi) * BK, m0);
-            tma_load_2d(smem + s * kStageBytes + kABytes, &g.b[j], &full[s], (kb0 + kbi) * BK, n0);
-          }
-          __syncwarp();
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          tma_load_2d(smem + s * kStageBytes, &g.a[j], &full[s], (kb0 + kbi) * BK, m0);
+          tma_load_2d(smem + s * kStageBytes + kABytes, &g.b[j], &full[s], (kb0 + kbi) * BK, n0);
           if (++s == NS) {
             s = 0;
             ph ^= 1u;
@@ -120,7 +117,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    {  // ---- MMA issuer ---------------------------------------------------------------------------------------
+    if (elect_one()) {  // ---- MMA issuer --------------------------------------------------------------------------
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       const uint32_t ring = smem_u32(smem);
       int s = 0;
@@ -138,19 +135,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
           }
         }
         tc_fence_after();
-        if (elect_one()) {
-          for (int pair = 0; pair < p.n_pairs; ++pair) {
-            const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
-            const uint64_t da = make_smem_desc_sw128(slot_addr[ai]), db = make_smem_desc_sw128(slot_addr[bi] + kABytes);
+        for (int pair = 0; pair < p.n_pairs; ++pair) {
+          const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
+          const uint64_t da = make_smem_desc_sw128(slot_addr[ai]), db = make_smem_desc_sw128(slot_addr[bi] + kABytes);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
-              mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kbi | pair | k) != 0);
-          }
-          for (int j = 0; j < T; ++j) mma_commit(&empty[slot_id[j]]);  // frees the slots once these MMAs have read them
-          if (kbi == n_kb - 1) mma_commit(tmem_full);
+          for (int k = 0; k < BK / 16; ++k)  // +32 B per 16-element K slice inside the swizzled 128 B row
+            mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kbi | pair | k) != 0);
         }
-        __syncwarp();
+        for (int j = 0; j < T; ++j) mma_commit(&empty[slot_id[j]]);  // frees the slots once these MMAs have read them
       }
+      mma_commit(tmem_full);
     }
   } else {  // ---- epilogue: warp quarter q owns TMEM lanes [32q, 32q+32) -----------------------------------
     mbar_wait(tmem_full, 0);

@@ -112,12 +112,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // The producer and issuer loops run on the WHOLE warp with one elected lane per asynchronous instruction: inside a
-  // divergent `lane == 0` region the compiler wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY
-  // loop (~80 clk per MMA, which made the issuing thread the bottleneck of the whole kernel); in warp-uniform code
-  // with elect.sync they issue back to back.
+  // The producer and issuer loops run on ONE lane chosen by elect.sync.  (Inside a `lane == 0` region the compiler cannot
+  // prove single-thread execution and wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop, ~80 clk per
+  // MMA, which made the issuing thread the bottleneck of the whole kernel; under an elect.sync predicate they issue
+  // back to back.)
   if (warp == 0) {
-    if (n_tiles > 0) {  // ---- TMA producer (both CTAs of a pair) --------------------------------------------------
+    if (n_tiles > 0 && elect_one()) {  // ---- TMA producer (both CTAs of a pair): ONE elected lane runs the loop -------
       int s = 0;            // ring slot and its phase, advanced incrementally (no integer division in the hot loops)
       uint32_t ph = 0;
       int tt_ = stagger;
@@ -126,16 +126,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
         if (++tt_ == n_tiles) tt_ = 0;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[s], ph ^ 1u);
-          if (elect_one()) {
-            if (PAIR) {
-              if (leader) mbar_arrive_expect_tx(&full[s], kTileBytes);  // both halves complete on the leader's barrier
-              tma_load_2d_pair(d_ring + (size_t)s * kSlotBytes, &p.d_map, mapa_shared(smem_u32(&full[s]), 0), kb * BK, d0);
-            } else {
-              mbar_arrive_expect_tx(&full[s], kTileBytes);
-              tma_load_2d(d_ring + (size_t)s * kSlotBytes, &p.d_map, &full[s], kb * BK, d0);
-            }
+          if (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&full[s], kTileBytes);  // both halves complete on the leader's barrier
+            tma_load_2d_pair(d_ring + (size_t)s * kSlotBytes, &p.d_map, mapa_shared(smem_u32(&full[s]), 0), kb * BK, d0);
+          } else {
+            mbar_arrive_expect_tx(&full[s], kTileBytes);
+            tma_load_2d(d_ring + (size_t)s * kSlotBytes, &p.d_map, &full[s], kb * BK, d0);
           }
-          __syncwarp();
           if (++s == NS) {
             s = 0;
             ph ^= 1u;
@@ -144,7 +141,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       }
     }
   } else if (warp == 1) {
-    if (n_tiles > 0 && leader) {  // ---- MMA issuer (leader CTA only) ---------------------------------------------------
+    if (n_tiles > 0 && leader && elect_one()) {  // ---- MMA issuer (leader CTA only), ONE elected lane -------------------
       constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TQ : TQ, TD);
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -160,28 +157,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint64_t db = make_smem_desc_sw128(r_addr + (uint32_t)s * kSlotBytes);
-          const bool last_kb = kb == KB - 1;
-          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              if (PAIR)
-                mma_bf16_ts_pair(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
-                                 (kb | k) != 0);
-              else
-                mma_bf16_ts(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
-                            (kb | k) != 0);
-            }
-            if (PAIR) mma_commit_pair(&empty[s], 3); else mma_commit(&empty[s]);
-            if (last_kb) {
-              if (PAIR) mma_commit_pair(&tmem_full[buf], 3); else mma_commit(&tmem_full[buf]);
-            }
+          for (int k = 0; k < BK / 16; ++k) {
+            if (PAIR)
+              mma_bf16_ts_pair(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
+                               (kb | k) != 0);
+            else
+              mma_bf16_ts(tmem_base + (uint32_t)(buf * TD), a_tmem + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc,
+                          (kb | k) != 0);
           }
-          __syncwarp();
+          if (PAIR) mma_commit_pair(&empty[s], 3); else mma_commit(&empty[s]);
           if (++s == NS) {
             s = 0;
             ph ^= 1u;
           }
         }
+        if (PAIR) mma_commit_pair(&tmem_full[buf], 3); else mma_commit(&tmem_full[buf]);
       }
     }
   } else {  // ---- epilogue: thread = query row, walks the 128 document scores of each finished tile ---------------
