@@ -666,6 +666,14 @@ static int get_forks(Forks** out) {
   *out = &f;
   return 0;
 }
+static int fwd1_products() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TT_FWD1_PRODUCTS");  // tuning hook: 3 = hi*hi + hi*lo + lo*hi only
+    v = (e && atoi(e) == 3) ? 3 : 6;
+  }
+  return v;
+}
 static int step_concurrency() {
   const char* e = getenv("TT_STEP_FORK");  // tuning hook: 0 = one serial chain
   return e ? atoi(e) : 1;
@@ -718,7 +726,7 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
     g[t].Ct_hi = w.ht_hi + tcol[t]; g[t].Ct_lo = w.ht_lo + tcol[t]; g[t].ldt = w.ldt;
   }
   // (6-product split for this layer only: its ReLU sign gates the backward, see mlp_fwd_sm100)
-  if ((rc = launch_gemm(g, 2, np == 3 ? 6 : 1, 1, nullptr, 0, st))) return rc;
+  if ((rc = launch_gemm(g, 2, np == 3 ? fwd1_products() : 1, 1, nullptr, 0, st))) return rc;
   // 4. y = h W2^T + b2
   for (int t = 0; t < 2; ++t) {
     g[t] = GemmDesc{};
