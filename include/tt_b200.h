@@ -265,6 +265,30 @@ int tt_peer_barrier(void* const* flags, int world, int rank, unsigned* ctl, tt_s
 int tt_peer_topk_merge(const float* const* parts_score, const int64_t* const* parts_id, int world, int Q, int k,
                        float* top_score, int64_t* top_id, tt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batch assembly on the device (backend/data.py:113-152 + the tokenizer padding of model.py:43-48, for a
+ * tokenised corpus resident in HBM — SURVEY.md §8f rank 1).  A token bank is ragged: `flat` holds the ids of all
+ * texts back to back (i64|i32|u16), text r occupies flat[offsets[r] .. offsets[r+1]).
+ *   pair_q / pair_d / pair_qid [n_pairs]: bank row of the query, bank row of the positive passage and the query id
+ *   of every (query, positive) pair of the dataset; order [Bg]: the dataset pairs that form this step's GLOBAL
+ *   batch (a slice of the epoch permutation); this rank assembles items [row0, row0 + B) of it.
+ *   Negative of item i = positive passage of item j, j uniform in [0, Bg) redrawn until j != i and
+ *   query_id[j] != query_id[i]; j is a pure function of (seed, i), so all ranks agree on the global batch's
+ *   negatives.  neg_out [B] (nullable) receives j.  err_flag (nullable) is set to 2 if an item has no partner.
+ *   Outputs: ids [B,Lq] / [B,Ld] / [B,Ld] (i64|i32|u16, zero padded, truncated to L) and masks (i64|i32|u8).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tt_token_bank {
+  const void* flat;
+  const int64_t* offsets;
+  int dtype;
+  int _pad;
+} tt_token_bank;
+int tt_assemble_triplets(const tt_token_bank* qbank, const tt_token_bank* dbank, const int32_t* pair_q,
+                         const int32_t* pair_d, const int32_t* pair_qid, const int32_t* order, int Bg, int row0,
+                         int B, uint64_t seed, int Lq, int Ld, void* q_ids, void* q_mask, void* p_ids, void* p_mask,
+                         void* n_ids, void* n_mask, int ids_dtype, int mask_dtype, int32_t* neg_out, int* err_flag,
+                         tt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -766,3 +766,109 @@ def test_document_search_engine_matches_cosine_ranking_and_persists(tt, tmp_path
     eng2 = search.DocumentSearchEngine(model=model, index_dir=str(tmp_path))
     assert eng2.get_index_info()["num_docs"] == 700
     assert [h["id"] for h in eng2.search(query, top_k=10)] == [h["id"] for h in res]
+
+
+# ---------------------------------------------------------------------------------------------------
+# batch assembly on the device (data.py:113-152 semantics for a token bank resident in HBM)
+# ---------------------------------------------------------------------------------------------------
+def _feeder_setup(tt, n_pairs=3000, B=256, world=1, rank=0, seed=3):
+    ds = tt.data.MSMarcoDataset("train", max_samples=n_pairs, synthetic=True)
+    torch.manual_seed(0)
+    m = tt.TwoTowersModel(projection_dim=64, precision="bf16x3").to(DEV)
+    tr = tt.training.FusedTrainer(m, 0.3, 1e-3, B // world, 32, 256, precision="bf16x3", token_slots=2,
+                                  ids_dtype=torch.uint16, mask_dtype=torch.uint8)
+    fd = tt.data.DeviceTripletFeeder(ds, B, 32, 256, DEV, rank=rank, world_size=world, seed=seed)
+    return ds, m, tr, fd
+
+
+def test_device_batch_assembly_matches_host_token_bank_and_negative_rule(tt):
+    B = 256
+    ds, m, tr, fd = _feeder_setup(tt, B=B)
+    fd.start_epoch()
+    counts = np.zeros(B, dtype=np.int64)
+    for step in range(min(4, len(fd))):
+        fd.assemble(tr, step % 2, step, want_neg=True)
+        torch.cuda.synchronize()
+        fd.check()
+        order = fd.order[step * B: (step + 1) * B].cpu().numpy()
+        neg = fd.neg.cpu().numpy()
+        qidx = np.array([int(ds.data[i]["query"].split(":")[1]) for i in order])
+        didx = np.array([int(ds.data[i]["positive"].split(":")[1]) for i in order])
+        qid = np.array([int(ds.data[i]["query_id"]) for i in order])
+        # the reference's rule: never itself, never a passage of the same query
+        assert (neg != np.arange(B)).all() and (qid[neg] != qid).all() and neg.min() >= 0 and neg.max() < B
+        counts += np.bincount(neg, minlength=B)
+        got = [t.cpu() for t in tr.tok_slots[step % 2]]
+        for (ids, mask), want in (((got[0], got[1]), ds.query_bank.batch(qidx, 32, 32)),
+                                  ((got[2], got[3]), ds.doc_bank.batch(didx, 256, 256)),
+                                  ((got[4], got[5]), ds.doc_bank.batch(didx[neg], 256, 256))):
+            assert torch.equal(ids.to(torch.int64), want.input_ids) and torch.equal(mask.to(torch.int64), want.attention_mask)
+        # a pure function of (seed, epoch, step): assembling again gives the same batch
+        before = [t.clone() for t in tr.tok_slots[step % 2]]
+        fd.assemble(tr, step % 2, step)
+        assert all(torch.equal(a, b) for a, b in zip(before, tr.tok_slots[step % 2]))
+    # roughly uniform choice of the partner (1024 draws over 256 bins: no bin should dominate)
+    assert counts.max() <= 16 and (counts > 0).sum() > 200
+
+
+def test_device_batch_assembly_rank_slices_agree_on_global_negatives(tt):
+    B = 256
+    ds, m, tr, fd = _feeder_setup(tt, B=B)
+    fd.start_epoch()
+    fd.assemble(tr, 0, 1, want_neg=True)
+    full = [t.clone() for t in tr.tok_slots[0]]
+    neg_full = fd.neg.clone()
+    for rank in range(4):
+        ds_r, m_r, tr_r, fd_r = _feeder_setup(tt, B=B, world=4, rank=rank)
+        fd_r.start_epoch()
+        assert torch.equal(fd_r.order, fd.order)  # same seed -> same permutation on every rank
+        fd_r.assemble(tr_r, 0, 1, want_neg=True)
+        lo, hi = rank * 64, (rank + 1) * 64
+        assert torch.equal(fd_r.neg, neg_full[lo:hi])
+        for a, b in zip(tr_r.tok_slots[0], full):
+            assert torch.equal(a, b[lo:hi])
+
+
+def test_train_epoch_device_equals_host_fed_training(tt):
+    """Same batches through the device feeder and through pinned host buffers -> bit-identical weights."""
+    B = 256
+    ds, m, tr, fd = _feeder_setup(tt, n_pairs=1500, B=B)
+    avg = tr.train_epoch_device(fd)
+    torch.cuda.synchronize()
+    assert 0.0 < avg < 0.5
+    # replay: rebuild the very same batches on the host from the feeder's permutation and negatives
+    ds2, m2, tr2, fd2 = _feeder_setup(tt, n_pairs=1500, B=B)
+    fd2.start_epoch()
+    assert torch.equal(fd2.order, fd.order)
+    for step in range(len(fd2)):
+        fd2.assemble(tr2, 0, step, want_neg=True)
+        torch.cuda.synchronize()
+        order, neg = fd2.order[step * B: (step + 1) * B].cpu().numpy(), fd2.neg.cpu().numpy()
+        qidx = np.array([int(ds.data[i]["query"].split(":")[1]) for i in order])
+        didx = np.array([int(ds.data[i]["positive"].split(":")[1]) for i in order])
+        kw = dict(ids_dtype=torch.uint16, mask_dtype=torch.uint8)
+        tr2.load_tokens(ds.query_bank.batch(qidx, 32, 32, **kw), ds.doc_bank.batch(didx, 256, 256, **kw),
+                        ds.doc_bank.batch(didx[neg], 256, 256, **kw), slot=1)
+        tr2.step(1)
+    torch.cuda.synchronize()
+    assert torch.equal(tr.flat_p, tr2.flat_p)
+
+
+@pytest.mark.parametrize("host_feeder", ["0", "1"])
+def test_run_training_end_to_end_readme_dev_shape(tt, monkeypatch, capsys, host_feeder):
+    """BASELINE configs[0] in small: run_training with the reference's signature on the synthetic corpus (fused step,
+    device- or host-assembled batches, validation NDCG@10 every epoch) returns a trained TwoTowersModel."""
+    monkeypatch.setenv("TT_SYNTHETIC_DATA", "1")
+    monkeypatch.setenv("TT_HOST_FEEDER", host_feeder)
+    torch.manual_seed(0)
+    model = tt.training.run_training(num_epochs=2, batch_size=256, learning_rate=1e-3, max_samples=3000,
+                                     projection_dim=64, margin=0.3, use_wandb=False, accumulation_steps=1,
+                                     use_mixed_precision=False, num_workers=0, run_comprehensive_test=False)
+    out = capsys.readouterr().out
+    assert isinstance(model, tt.TwoTowersModel) and "Fused B200 step: True" in out
+    losses = [float(l.split(":")[1]) for l in out.splitlines() if l.startswith("Average training loss")]
+    ndcgs = [float(l.split(":")[1]) for l in out.splitlines() if l.startswith("Validation NDCG@10")]
+    assert len(losses) == 2 and len(ndcgs) == 2 and all(np.isfinite(losses)) and all(0.0 <= n <= 1.0 for n in ndcgs)
+    assert losses[0] < 0.35  # random init starts at the margin (0.3); training must not blow up
+    sd = model.state_dict()
+    assert tuple(sd["query_tower.projection.2.weight"].shape) == (64, 64)

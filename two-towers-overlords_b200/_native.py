@@ -36,6 +36,10 @@ class PoolSeg(ctypes.Structure):
                 ("row0", c_int), ("_pad", c_int)]
 
 
+class TokenBankDesc(ctypes.Structure):
+    _fields_ = [("flat", c_void_p), ("offsets", c_void_p), ("dtype", c_int), ("_pad", c_int)]
+
+
 class StepArgs(ctypes.Structure):
     _fields_ = [
         ("q_ids", c_void_p), ("q_mask", c_void_p), ("Lq", c_int),
@@ -102,6 +106,9 @@ _SIGNATURES = {
     "tt_dp_segment_bytes": (c_size_t, [c_size_t, c_int]),
     "tt_dp_reduce_adam": (c_int, [POINTER(c_void_p), c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_float,
                                   c_float, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "tt_assemble_triplets": (c_int, [POINTER(TokenBankDesc), POINTER(TokenBankDesc), c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int, c_int, c_int, ctypes.c_uint64, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_peer_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
     "tt_peer_topk_merge": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),

@@ -15,6 +15,7 @@ Datasets and triplet batching — drop-in for the reference's backend/data.py su
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 import random
@@ -271,3 +272,78 @@ class TokenTripletLoader:
             yield (self.ds.query_bank.batch(self.q_idx[g[mine]], self.Lq, self.Lq, **kw),
                    self.ds.doc_bank.batch(self.d_idx[g[mine]], self.Ld, self.Ld, **kw),
                    self.ds.doc_bank.batch(self.d_idx[neg[mine]], self.Ld, self.Ld, **kw))
+
+
+class DeviceTripletFeeder:
+    """Batch assembly on the device: the tokenised dataset lives in HBM as two ragged token
+    banks; every step ONE kernel (`tt_assemble_triplets`) turns a slice of the epoch permutation into the six padded
+    token tensors of a FusedTrainer slot and draws the in-batch negatives (same rule as backend/data.py:124-137) — no
+    host work and no H2D traffic per step.  Under data parallelism every rank holds the banks, uses the same epoch
+    permutation (same seed) and assembles only its slice of the global batch; the negatives are a pure function of
+    (seed, position in the global batch), so the ranks agree without communicating."""
+
+    def __init__(self, dataset: MSMarcoDataset, global_batch: int, Lq: int = 32, Ld: int = 256, device="cuda",
+                 rank: int = 0, world_size: int = 1, seed: int = 0, drop_last: bool = True):
+        assert dataset.query_bank is not None, "DeviceTripletFeeder needs a token-bank dataset"
+        assert global_batch % world_size == 0 and global_batch >= 2
+        try:
+            from . import _native as N
+        except ImportError:
+            import _native as N
+        self.N = N
+        N.ensure_sm100()
+        self.device = torch.device(device)
+        self.gb, self.Lq, self.Ld = int(global_batch), int(Lq), int(Ld)
+        self.rank, self.world, self.seed = int(rank), int(world_size), int(seed)
+        self.per = self.gb // self.world
+        if not drop_last:
+            raise ValueError("DeviceTripletFeeder assembles fixed-shape batches only (drop_last=True)")
+
+        def upload(bank: TokenBank):
+            small = int(bank.flat.max(initial=0)) < 65536
+            flat = torch.from_numpy(bank.flat.astype(np.uint16 if small else np.int32)).to(self.device)
+            off = torch.from_numpy(bank.offsets.astype(np.int64)).to(self.device)
+            desc = N.TokenBankDesc(flat.data_ptr(), off.data_ptr(), N.dtype_code(flat), 0)
+            return flat, off, desc
+
+        self.q_flat, self.q_off, self.q_desc = upload(dataset.query_bank)
+        self.d_flat, self.d_off, self.d_desc = upload(dataset.doc_bank)
+        as_dev = lambda a: torch.from_numpy(np.asarray(a, dtype=np.int32)).to(self.device)  # noqa: E731
+        self.pair_q = as_dev([int(d["query"].split(":")[1]) for d in dataset.data])
+        self.pair_d = as_dev([int(d["positive"].split(":")[1]) for d in dataset.data])
+        self.pair_qid = as_dev([int(d["query_id"]) for d in dataset.data])
+        self.n = len(dataset.data)
+        self.gen = torch.Generator(device=self.device).manual_seed(self.seed)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.neg = torch.zeros(self.per, dtype=torch.int32, device=self.device)
+        self.order = None
+        self.epoch = 0
+
+    def __len__(self):
+        return self.n // self.gb
+
+    def start_epoch(self):
+        """New shuffle (DataLoader(shuffle=True), data.py:105); the same on every rank because the seed is."""
+        self.order = torch.randperm(self.n, generator=self.gen, device=self.device).to(torch.int32)
+        self.epoch += 1
+
+    def assemble(self, trainer, slot: int, step: int, want_neg: bool = False):
+        """Fills trainer.tok_slots[slot] with the batch of `step` (asynchronous, current stream)."""
+        N = self.N
+        assert self.order is not None, "call start_epoch() first"
+        assert 0 <= step < len(self)
+        q_ids, q_mask, p_ids, p_mask, n_ids, n_mask = trainer.tok_slots[slot]
+        assert tuple(q_ids.shape) == (self.per, self.Lq) and tuple(p_ids.shape) == (self.per, self.Ld)
+        order = self.order[step * self.gb: (step + 1) * self.gb]
+        step_seed = (self.seed * 0x9E3779B1 + self.epoch * 0x85EBCA77 + step) & 0xFFFFFFFFFFFFFFFF
+        N.check(N.load().tt_assemble_triplets(
+            ctypes.byref(self.q_desc), ctypes.byref(self.d_desc), N.ptr(self.pair_q), N.ptr(self.pair_d),
+            N.ptr(self.pair_qid), order.data_ptr(), self.gb, self.rank * self.per, self.per, step_seed, self.Lq, self.Ld,
+            N.ptr(q_ids), N.ptr(q_mask), N.ptr(p_ids), N.ptr(p_mask), N.ptr(n_ids), N.ptr(n_mask), N.dtype_code(q_ids),
+            N.dtype_code(q_mask), N.ptr(self.neg) if want_neg else None, N.ptr(self.err), N.stream()),
+            "tt_assemble_triplets")
+
+    def check(self):
+        """Host sync: raises if some item had no eligible in-batch negative (the reference would loop forever)."""
+        if int(self.err.item()) != 0:
+            raise ValueError("batch has an item with no in-batch negative (all query_ids equal)")

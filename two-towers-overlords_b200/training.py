@@ -25,12 +25,12 @@ from torch import GradScaler, autocast
 
 try:
     from . import comm, ops
-    from .data import MSMarcoDataset, TokenTripletLoader, TripletDataLoader
+    from .data import DeviceTripletFeeder, MSMarcoDataset, TokenTripletLoader, TripletDataLoader
     from .model import TokenBatch, TripletLoss, TwoTowersModel
 except ImportError:
     import comm
     import ops
-    from data import MSMarcoDataset, TokenTripletLoader, TripletDataLoader
+    from data import DeviceTripletFeeder, MSMarcoDataset, TokenTripletLoader, TripletDataLoader
     from model import TokenBatch, TripletLoss, TwoTowersModel
 
 try:  # wandb is optional at import time; only touched when logging is requested
@@ -359,6 +359,31 @@ class FusedTrainer:
             self._parity ^= 1
         self.steps_done += 1
         return self.loss_view[0]
+
+    def train_epoch_device(self, feeder, log_every: int = 0) -> float:
+        """One pass with batches assembled on the device (data.DeviceTripletFeeder): per step one assembly kernel for
+        the NEXT batch, then the step graph — the host only launches."""
+        steps = len(feeder)
+        if steps == 0:
+            raise ZeroDivisionError("FusedTrainer.train_epoch_device: not enough pairs for one batch")
+        feeder.start_epoch()
+        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        n_slots = len(self.tok_slots)
+        feeder.assemble(self, 0, 0)
+        for i in range(steps):
+            slot = i % n_slots if n_slots >= 2 else 0
+            nslot = None
+            if i + 1 < steps and n_slots >= 2:
+                nslot = (i + 1) % n_slots
+                feeder.assemble(self, nslot, i + 1)
+            loss = self.step(slot, nslot)
+            total += loss.double()
+            if i + 1 < steps and n_slots < 2:
+                feeder.assemble(self, 0, i + 1)
+            if log_every and (i + 1) % log_every == 0:
+                print(f"Batch {i + 1}, Loss: {loss.item():.4f}")
+        feeder.check()
+        return float(total.item()) / steps
 
     # -- checkpoint / resume (main.py:142-152 saves `model.state_dict()`; this adds the optimiser so a run can resume) --
     def _slice_bounds(self):
@@ -729,15 +754,21 @@ def run_training(
     print(f"  Fused B200 step: {fused}")
 
     scaler = GradScaler(device.type) if use_mixed_precision else None
-    trainer = token_dl = None
+    trainer = token_dl = feeder = None
     if fused:
         trainer = FusedTrainer(model, margin, learning_rate, batch_size, token_slots=2)
-        token_dl = TokenTripletLoader(train_ds, batch_size, trainer.Lq, trainer.Ld)
+        if os.environ.get("TT_HOST_FEEDER") == "1" or len(train_ds) < 2 * batch_size:
+            token_dl = TokenTripletLoader(train_ds, batch_size, trainer.Lq, trainer.Ld)  # host-assembled batches
+        else:  # token bank resident in HBM, batches (and in-batch negatives) assembled by one kernel per step
+            feeder = DeviceTripletFeeder(train_ds, batch_size, trainer.Lq, trainer.Ld, device,
+                                         seed=random.randrange(2 ** 31))
 
     print(f"Starting training for {num_epochs} epochs...")
     for epoch in range(num_epochs):
         print(f"\nEpoch {epoch + 1}/{num_epochs}")
-        if trainer is not None:
+        if trainer is not None and feeder is not None:
+            avg_loss = trainer.train_epoch_device(feeder, log_every=10)
+        elif trainer is not None:
             avg_loss = trainer.train_epoch(token_dl, log_every=10)
         elif use_mixed_precision and scaler is not None:
             avg_loss = train_epoch_optimized(model=model, dataloader=train_dl, criterion=criterion,
