@@ -60,6 +60,23 @@ assert sq and torch.equal(pq, pp), "pipelined peer exchange differs from the ste
 assert sp, "peer exchange left the replicas different"
 assert err < 1e-5, err
 assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(ln, lp))
+# corpus-scan list merge over peer memory vs all-gather + tt_topk_merge
+from two_towers_overlords_b200 import comm, retrieval  # noqa: E402
+
+Q, k = 5000, 10
+g = torch.Generator(device=dev).manual_seed(77 + rank)
+top_s = torch.randn(Q, k, generator=g, device=dev).sort(dim=1, descending=True).values
+top_i = (torch.arange(Q * k, device=dev).reshape(Q, k) * world + rank)
+peer = comm.PeerLists(Q, k, world, rank, dev)
+for rep in range(3):
+    a_s, a_i = retrieval.gather_and_merge(top_s + rep, top_i, world)
+    b_s, b_i = retrieval.gather_and_merge(top_s + rep, top_i, world, peer=peer)
+    torch.cuda.synchronize()
+    peer.check()
+    assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s), "peer list merge differs from all-gather + merge"
+dist.barrier()
+peer.close()
 if rank == 0:
+    print("peer list merge == all-gather + merge")
     print("OK")
 dist.destroy_process_group()

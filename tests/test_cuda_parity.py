@@ -872,3 +872,61 @@ def test_run_training_end_to_end_readme_dev_shape(tt, monkeypatch, capsys, host_
     assert losses[0] < 0.35  # random init starts at the margin (0.3); training must not blow up
     sd = model.state_dict()
     assert tuple(sd["query_tower.projection.2.weight"].shape) == (64, 64)
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_peer_list_merge_virtual_ranks_equals_topk_merge(tt, world):
+    """tt_peer_barrier + tt_peer_topk_merge (lists read in place from every rank's segment) == tt_topk_merge of the
+    gathered lists, ties by ascending id, -1 ids ignored; `world` ranks on one device, one stream each."""
+    from two_towers_overlords_b200 import comm
+
+    torch.manual_seed(world)
+    Q, k = 300, 10
+    pls = comm.PeerLists.virtual_ranks(Q, k, world, DEV)
+    parts_s = torch.randn(world, Q, k, device=DEV).sort(dim=2, descending=True).values
+    parts_s[:, ::7, 3:5] = 0.25  # ties across and inside lists
+    parts_s = parts_s.sort(dim=2, descending=True).values
+    parts_i = torch.stack([torch.arange(Q * k, device=DEV).reshape(Q, k) * world + r for r in range(world)])
+    parts_i[-1, ::5, 7:] = -1    # a short shard
+    want_s, want_i = tt.ops.topk_merge(parts_s, parts_i)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    outs = []
+    try:
+        for rep in range(2):  # twice: the epoch counters of the barriers must advance
+            outs = []
+            for r, (pl, st) in enumerate(zip(pls, streams)):
+                with torch.cuda.stream(st):
+                    outs.append(pl.merge(parts_s[r], parts_i[r]))
+            torch.cuda.synchronize()
+            for pl, (s_, i_) in zip(pls, outs):
+                pl.check()
+                assert torch.equal(i_, want_i) and torch.equal(s_[want_i >= 0], want_s[want_i >= 0])
+    finally:
+        for pl in pls:
+            pl.close()
+
+
+def test_scan_streaming_regime_is_repeatable_under_stress(tt):
+    """128 queries against a 2.2 M-document shard (147 document splits, an odd number of tiles per CTA, a 9-slot ring
+    that is not a multiple of the 6 k-blocks of a tile), 600 back-to-back searches: every one must return the ids of
+    the first and the kernel must never trap (a two-issuer variant of the kernel failed exactly here)."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    De = torch.randn(2_200_000, 384, generator=g, device=DEV)
+    Qe = torch.randn(128, 384, generator=g, device=DEV)
+    shard = tt.retrieval.CorpusShard(De, precision="bf16")
+    del De
+    ref_s, ref_i = shard.search(Qe, 10)
+    torch.cuda.synchronize()
+    for it in range(600):
+        s, i = shard.search(Qe, 10)
+        if it % 100 == 99:
+            torch.cuda.synchronize()
+            assert torch.equal(i, ref_i) and torch.equal(s, ref_s)
+    # and the list is the exact one: fp32 scan of the same shard (ids may only differ inside a near-tie, gap <= 1e-5)
+    s32, i32 = tt.ops.scan_topk(tt.ops.l2_normalize_rows(Qe), shard.Dn, k=11, precision="fp32")
+    s32, i32, got_i, got_s = s32.cpu().numpy(), i32.cpu().numpy(), ref_i.cpu().numpy(), ref_s.cpu().numpy()
+    assert np.allclose(got_s, s32[:, :10], atol=1e-5)
+    for q, r in zip(*np.nonzero(got_i != i32[:, :10])):
+        gaps = [abs(s32[q, r] - s32[q, r + 1])] + ([abs(s32[q, r] - s32[q, r - 1])] if r else [])
+        assert min(gaps) <= 1e-5, (q, r, gaps)

@@ -140,3 +140,62 @@ class DpExchange:
 
     def close(self):
         self.own.close()
+
+
+class PeerLists:
+    """Per-shard top-k lists of the corpus scan kept in peer memory: every rank writes its [Q,k]
+    (score f32, id i64) list into its own segment, then `merge()` = barrier -> `tt_peer_topk_merge` (each rank reads
+    all lists in place over NVLink and merges by (score desc, id asc)) -> barrier.  Replaces the all-gather + merge."""
+
+    def __init__(self, Q: int, k: int, world: int, rank: int, device, segments: Optional[List[int]] = None,
+                 own: Optional[PeerSegment] = None, group=None):
+        self.Q, self.k, self.world, self.rank, self.device = int(Q), int(k), int(world), int(rank), torch.device(device)
+        self.off_id = (self.Q * self.k * 4 + 255) // 256 * 256
+        self.off_flag = self.off_id + (self.Q * self.k * 8 + 255) // 256 * 256
+        self.nbytes = self.off_flag + 256
+        self.own = own if own is not None else PeerSegment(self.nbytes, self.device)
+        if segments is None:
+            if self.world > 1:
+                handles = exchange_handles(self.own.handle, self.world, group)
+                segments = [self.own.ptr if r == self.rank else self.own.open_peer(handles[r]) for r in range(self.world)]
+                torch.distributed.barrier(group=group)
+            else:
+                segments = [self.own.ptr]
+        arr = lambda off: (c_void_p * self.world)(*[c_void_p(int(s_) + off) for s_ in segments])  # noqa: E731
+        self.p_score, self.p_id, self.p_flag = arr(0), arr(self.off_id), arr(self.off_flag)
+        self.score = self.own.tensor(0, (self.Q, self.k), torch.float32)
+        self.ids = self.own.tensor(self.off_id, (self.Q, self.k), torch.int64)
+        self.ctl = torch.zeros(4, dtype=torch.int32, device=self.device)
+
+    @classmethod
+    def virtual_ranks(cls, Q: int, k: int, world: int, device) -> List["PeerLists"]:
+        probe = cls.__new__(cls)
+        off_id = (Q * k * 4 + 255) // 256 * 256
+        nbytes = off_id + (Q * k * 8 + 255) // 256 * 256 + 256
+        owns = [PeerSegment(nbytes, device) for _ in range(world)]
+        ptrs = [o.ptr for o in owns]
+        del probe
+        return [cls(Q, k, world, r, device, segments=ptrs, own=owns[r]) for r in range(world)]
+
+    def barrier(self):
+        N.check(N.load().tt_peer_barrier(self.p_flag, self.world, self.rank, N.ptr(self.ctl), N.stream()),
+                "tt_peer_barrier")
+
+    def merge(self, top_s: torch.Tensor, top_i: torch.Tensor):
+        """This rank's shard list [Q,k] -> the global [Q,k] (same on every rank).  Asynchronous on the current stream."""
+        self.score.copy_(top_s)
+        self.ids.copy_(top_i)
+        out_s = torch.empty(self.Q, self.k, dtype=torch.float32, device=self.device)
+        out_i = torch.empty(self.Q, self.k, dtype=torch.int64, device=self.device)
+        self.barrier()  # every list complete
+        N.check(N.load().tt_peer_topk_merge(self.p_score, self.p_id, self.world, self.Q, self.k, N.ptr(out_s),
+                                            N.ptr(out_i), N.stream()), "tt_peer_topk_merge")
+        self.barrier()  # nobody overwrites a list that a peer is still reading
+        return out_s, out_i
+
+    def check(self):
+        if int(self.ctl[3].item()) != 0:
+            raise N.NativeError("peer barrier timed out waiting for another rank")
+
+    def close(self):
+        self.own.close()

@@ -29,7 +29,7 @@ using bf16 = __nv_bfloat16;
 using namespace ptx;
 
 constexpr int TQ = 128, TD = 128, BK = 64;
-constexpr int kScanThreads = 224;  // warp 0 TMA producer, warp 1 + warp 6 MMA issuers, warps 2-5 epilogue
+constexpr int kScanThreads = 192;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 constexpr uint32_t kTileBytes = TD * BK * 2;  // 16 KB: one 128-row x 64-k bf16 tile (queries or documents)
 constexpr int kMaxKC = 48;
 constexpr int kSlack = 64;  // append room beyond KC: a compaction runs when fewer than 32 (one TMEM chunk) slots remain
@@ -140,15 +140,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
         }
       }
     }
-  } else if (warp == 1 || warp == 6) {
-    // TWO issuers on alternating tiles (warp 1: even tiles -> accumulator 0, warp 6: odd tiles -> accumulator 1).  One
-    // thread needs ~300 clk of address arithmetic, barrier polls and issue slots per k-block against 256 clk of MMA
-    // time, so a single issuer leaves the tensor pipe ~25 % idle (ncu: 73 % active); two keep it fed.  Each walks the
-    // ring in the global k-block order but only touches its own tiles' slots; tcgen05.commit tracks the issuing
-    // thread's MMAs, so slot releases stay exact.
-    constexpr int kIssuers = PAIR ? 1 : 2;
-    const int me = warp == 1 ? 0 : 1;
-    if (n_tiles > 0 && leader && me < kIssuers && elect_one()) {
+  } else if (warp == 1) {
+    // (A second issuing thread on alternating tiles was tried: no gain — the batched scan runs at the power cap —
+    // and with parity-only mbarrier waits an issuer that gets a whole ring round ahead of the other mistakes an old
+    // phase of a slot for the new one, so there is exactly one issuer.)
+    if (n_tiles > 0 && leader && elect_one()) {  // ---- MMA issuer (leader CTA only), ONE elected lane -------------------
       constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TQ : TQ, TD);
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -156,15 +152,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       const uint32_t a_tmem = tmem_base + (uint32_t)(2 * TD);
       int s = 0;
       uint32_t ph = 0;
-      auto skip_tile = [&]() {  // advance over the other issuer's KB slots
-        s += KB;
-        while (s >= NS) {
-          s -= NS;
-          ph ^= 1u;
-        }
-      };
-      if (me == 1) skip_tile();
-      for (int t = me; t < n_tiles; t += kIssuers) {
+      for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
         mbar_wait(&tmem_empty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue(s) drained this accumulator
         tc_fence_after();
@@ -188,7 +176,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
           }
         }
         if (PAIR) mma_commit_pair(&tmem_full[buf], 3); else mma_commit(&tmem_full[buf]);
-        if (kIssuers == 2) skip_tile();
       }
     }
   } else {  // ---- epilogue: thread = query row, walks the 128 document scores of each finished tile ---------------

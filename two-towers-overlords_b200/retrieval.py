@@ -62,10 +62,13 @@ def all_gather_lists(top_s: torch.Tensor, top_i: torch.Tensor, world_size: int, 
     return parts_s, parts_i
 
 
-def gather_and_merge(top_s: torch.Tensor, top_i: torch.Tensor, world_size: int, group=None):
-    """All-gather the per-shard lists [Q,k] and merge them to the global top-k on every rank."""
+def gather_and_merge(top_s: torch.Tensor, top_i: torch.Tensor, world_size: int, group=None, peer=None):
+    """All-gather the per-shard lists [Q,k] and merge them to the global top-k on every rank.  `peer`
+    (comm.PeerLists) merges them in place over NVLink peer memory instead of the NCCL all-gather."""
     if world_size == 1:
         return top_s, top_i
+    if peer is not None:
+        return peer.merge(top_s, top_i)
     return ops.topk_merge(*all_gather_lists(top_s, top_i, world_size, group))
 
 
@@ -78,9 +81,9 @@ def relevance_csr(relevant: Sequence[Sequence[int]], device) -> tuple[torch.Tens
 
 
 def retrieve_and_score(shard: CorpusShard, query_embeds: torch.Tensor, relevant_csr, k: int = 10,
-                       world_size: int = 1, group=None):
+                       world_size: int = 1, group=None, peer=None):
     """Top-k ids of every query over the whole (sharded) corpus and their NDCG@k."""
     top_s, top_i = shard.search(query_embeds, k)
-    top_s, top_i = gather_and_merge(top_s, top_i, world_size, group)
+    top_s, top_i = gather_and_merge(top_s, top_i, world_size, group, peer)
     ndcg = ops.ndcg_at_k(top_i, relevant_csr[0], relevant_csr[1], kk=k)
     return top_s, top_i, ndcg

@@ -337,6 +337,8 @@ class FusedTrainer:
         its pooled gather then runs beside this step and the following step(next_slot, ...) skips it."""
         if not self._warm:
             self._warm_up()
+        if self.train_table:
+            next_slot = None  # a trainable table changes between steps: its gather cannot run ahead of the update
         lib = ops.N.load()
         parity = self._parity
         if self._primed != slot:  # pipeline start (or a schedule change): this step's gather has not run yet
