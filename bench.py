@@ -130,6 +130,10 @@ def cpu_train_throughput(budget_s: float, steps: int | None = None, warmup: int 
     from oracle import two_towers_oracle as O
 
     torch.manual_seed(0)
+    try:  # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        pass
     threads = torch.get_num_threads()
     model = O.OracleTwoTowers(P_DIM, vocab=VOCAB, hidden=HIDDEN)
     opt = torch.optim.Adam(model.parameters(), lr=LR)
