@@ -1,5 +1,4 @@
-"""Timing probe (results are NOT numerically meaningful: the two branches race on the activation buffers):
-how long does a step take when the pooled gather of the next step runs beside the rest of the current one?"""
+"""Diagnostic: gather/rest overlap with the rest of the step on a high-priority stream (timing only)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,39 +7,35 @@ from two_towers_overlords_b200.training import FusedTrainer
 
 dev = torch.device("cuda")
 torch.manual_seed(0)
-B, P = 2048, 512
+B, P, NSLOT = 2048, 512, 8
 model = TwoTowersModel(projection_dim=P, precision="bf16x3").to(dev)
-tr = FusedTrainer(model, 0.3, 1e-3, B, 32, 256, precision="bf16x3", use_graph=False, token_slots=8)
-for slot in range(8):
+tr = FusedTrainer(model, 0.3, 1e-3, B, 32, 256, precision="bf16x3", use_graph=False, token_slots=NSLOT)
+for slot in range(NSLOT):
     for t in tr.tok_slots[slot]:
         if t.dtype == torch.uint8: t.fill_(1)
         else: t.copy_(torch.randint(999, 30522, t.shape, device=dev).to(t.dtype))
-side = torch.cuda.Stream(priority=int(sys.argv[1]) if len(sys.argv) > 1 else 0)
-main = torch.cuda.current_stream()
-
-def seq(slot):
-    tr._fwd_bwd(slot, 1); tr._fwd_bwd(slot, 2); tr._optimizer()
-def ovl(slot):
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        tr._fwd_bwd((slot + 1) % 8, 1)
-    tr._fwd_bwd(slot, 2); tr._optimizer()
-    main.wait_stream(side)
-def only_back(slot):
-    tr._fwd_bwd(slot, 2); tr._optimizer()
-def only_front(slot):
-    tr._fwd_bwd(slot, 1)
-
-for name, fn in (("sequential", seq), ("overlapped", ovl), ("back only", only_back), ("front only", only_front)):
-    for i in range(3): fn(i % 8)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for i in range(8): fn(i)
-    for _ in range(3): g.replay()
+tr._warm_up()
+def timeit(name, fn, n=20):
+    for i in range(3): fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(20): g.replay()
+    for i in range(n): fn(i)
     e1.record(); torch.cuda.synchronize()
-    print(f"{name}: {e0.elapsed_time(e1) / 160 * 1e3:.1f} us/step")
+    print(f"{name}: {e0.elapsed_time(e1) / n / NSLOT * 1e3:.1f} us/step", flush=True)
+
+for cap_prio, side_prio in ((0, 0), (-1, 0), (0, -1)):
+    cap = torch.cuda.Stream(priority=cap_prio)
+    tr.side = torch.cuda.Stream(priority=side_prio)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=cap):
+        for s in range(NSLOT): tr._pipelined(s, (s + 1) % NSLOT, s & 1)
+    timeit(f"capture prio {cap_prio}, gather prio {side_prio}", lambda i: g.replay())
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for s in range(NSLOT): tr._pipelined(s, None, 0)
+timeit("rest only", lambda i: g.replay())
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for s in range(NSLOT): tr._fwd_bwd(s, 1, 0)
+timeit("gather only", lambda i: g.replay())

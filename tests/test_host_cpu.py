@@ -238,3 +238,56 @@ def test_search_model_discovery_follows_reference_rules(pkg, tmp_path):
     torch.save({"other": torch.zeros(1)}, tmp_path / "weights.pt")
     path, fname = search.find_best_model(str(tmp_path))
     assert fname == "weights.pt" and search.get_projection_dim_from_model(path) == search.DEFAULT_PROJ_DIM
+
+
+def test_ctypes_signatures_match_the_header_prototypes(pkg):
+    """Every prototype in include/tt_b200.h has a ctypes signature with the same number of parameters (binding
+    drift shows up here, not as a crash on the GPU box)."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "tt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = dict(re.findall(r"\b(tt_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text))
+    sigs = pkg._native._SIGNATURES
+    assert set(protos) == set(sigs), set(protos) ^ set(sigs)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(sigs[name][1]), (name, n, len(sigs[name][1]))
+
+
+def test_step_args_struct_matches_the_header(pkg):
+    """tt_step_args: the ctypes mirror lists the same fields in the same order as the C struct."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "tt_b200.h")).read()
+    body = re.search(r"typedef struct tt_step_args \{(.*?)\} tt_step_args;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", " ", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            names.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+    assert names == [f[0] for f in pkg._native.StepArgs._fields_]
+
+
+def test_reference_arm_prints_one_json_line_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) works without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_triplets_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
