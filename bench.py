@@ -316,6 +316,20 @@ def run_b200(args):
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
     e2e_value = B_PER_GPU * world * K / (e2e_ms * 1e-3)
 
+    # ---- the same step with nothing overlapped (gather, then the chain): the denominator that is comparable with
+    # ncu's serialised launch list when quoting the gather's share of a step -------------------------------------
+    for i in range(8):
+        trainer.step(i % 8, None)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    n_seq = max(16, min(K, 64))
+    for i in range(n_seq):
+        trainer.step(i % 8, None)
+    ev1.record()
+    torch.cuda.synchronize()
+    seq_ms = ev0.elapsed_time(ev1) / n_seq
+
     # ---- roofline of the dominant kernel: the pooled gather, timed alone on the launching stream -----
     esz = 2 if table_dtype == torch.bfloat16 else 4
     tok_per_triplet = LQ + 2 * LD
@@ -356,8 +370,10 @@ def run_b200(args):
         "traffic": ncu_traffic("pool_fwd_kernel") if table_dtype == torch.float32 else None,
         "algorithmic_bytes_per_launch": alg_bytes_per_triplet * B_PER_GPU, "us_per_launch": pool_ms * 1e3,
         "share_of_step": pool_ms / (ms_total / K),
+        "share_of_serialised_step": pool_ms / seq_ms, "serialised_step_ms": seq_ms,
         "share_note": "timed alone; inside a step this kernel (for step i+1) runs BESIDE the tensor-core chain of "
-                      "step i, so the shares of the two do not add up to 1",
+                      "step i, so the shares of the two do not add up to 1; share_of_serialised_step divides by the "
+                      "step time with nothing overlapped and is the figure to compare with the ncu launch list",
         "note": "both 46.9 MB fp32 tables fit the 126 MB L2, so DRAM traffic is far below the algorithmic bytes "
                 "and frac can exceed 1 (SURVEY.md §7); see profiles/ for dram__bytes and L2 throughput",
     }

@@ -701,6 +701,7 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
   if (front) {
     PoolParams pp = s.pool;
     pp.x_hi = w.x_hi; pp.x_lo = w.x_lo; pp.x_lo2 = (np == 3) ? w.x_lo2 : nullptr; pp.xt_hi = nullptr; pp.xt_lo = nullptr;
+    pp.share_sm = (s.phases == TT_STEP_FRONT) ? 1 : 0;  // gather-only call = the pipelined trainer's look-ahead gather
     if ((rc = pool_fwd_launch(pp, s.table_dtype, H, st))) return rc;
     if ((rc = transpose_pair(w.x_hi, w.x_lo, 3 * B, H, w.xt_hi, w.xt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
   }

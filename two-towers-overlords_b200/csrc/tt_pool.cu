@@ -246,14 +246,31 @@ int pool_variant() {
   return v;
 }
 
+// Unused dynamic shared memory that caps how many gather CTAs an SM holds.  When the gather of step i+1 runs beside the
+// tensor-core chain of step i (p.share_sm), an SM full of gather CTAs (36 warps, ~62 K registers) leaves no room for
+// a GEMM CTA until a whole wave of gathers has retired: the chain — the critical path — then stalls ~60 us per step
+// (torch.profiler timeline).  Fewer resident gather CTAs cost the gather some latency hiding, which does not matter
+// because it runs in the chain's shadow.
+size_t pool_pad_smem(bool share_sm) {
+  static int pad = -1;
+  if (pad < 0) {
+    const char* e = getenv("TT_POOL_PAD_SMEM");  // tuning hook (bytes, <= 40960)
+    pad = e ? atoi(e) : kPoolSharePadBytes;
+    if (pad < 0) pad = 0;
+    if (pad > 40960) pad = 40960;
+  }
+  return share_sm ? (size_t)pad : 0;
+}
+
 template <typename TE, int NV>
 int launch_pool(const PoolParams& p, int total, cudaStream_t st) {
   constexpr int UNROLL = sizeof(TE) == 4 ? 4 : 8;
+  const size_t pad = pool_pad_smem(p.share_sm != 0);
   switch (pool_variant()) {
-    case 1: pool_fwd_kernel<TE, NV, UNROLL, false><<<total, kPoolThreads, 0, st>>>(p); break;
-    case 2: pool_fwd_kernel<TE, NV, UNROLL * 2, false><<<total, kPoolThreads, 0, st>>>(p); break;
-    case 3: pool_fwd_kernel<TE, NV, UNROLL / 2, true><<<total, kPoolThreads, 0, st>>>(p); break;
-    default: pool_fwd_kernel<TE, NV, UNROLL, true><<<total, kPoolThreads, 0, st>>>(p); break;
+    case 1: pool_fwd_kernel<TE, NV, UNROLL, false><<<total, kPoolThreads, pad, st>>>(p); break;
+    case 2: pool_fwd_kernel<TE, NV, UNROLL * 2, false><<<total, kPoolThreads, pad, st>>>(p); break;
+    case 3: pool_fwd_kernel<TE, NV, UNROLL / 2, true><<<total, kPoolThreads, pad, st>>>(p); break;
+    default: pool_fwd_kernel<TE, NV, UNROLL, true><<<total, kPoolThreads, pad, st>>>(p); break;
   }
   TT_LAUNCH_CHECK();
   return 0;

@@ -29,7 +29,10 @@ struct PoolParams {
   // column of row r in the transposed copies: r + (r >= t_split_row ? t_shift : 0) — lets the document rows
   // start at a 64-aligned column so each tower's K range is its own TMA tensor
   int t_split_row, t_shift;
+  int share_sm;  // 1: this launch runs beside other kernels (pipelined step): cap the resident CTAs per SM
 };
+
+constexpr int kPoolSharePadBytes = 0;  // default cap (bytes of unused dynamic smem per CTA); tuned on B200, see tt_pool.cu
 
 int pool_fwd_launch(PoolParams p, int table_dtype, int H, cudaStream_t st);
 
