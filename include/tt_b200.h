@@ -250,7 +250,7 @@ size_t tt_dp_segment_bytes(size_t n_param, int world);
  *   state: 4 doubles {t, beta1^t, beta2^t, -}; ctl: 16 u32 {epoch, ticket, ticket, error, then four u64
  *   diagnostics: ns until all gradient flags, ns from there to kernel end, calls, ns of the own push}, both
  *   zero-initialised, local.  ctl[3] != 0 after a call means a peer did not answer within 4 s.
- *   max_ctas: upper bound on the CTAs used (<= SM count; 0 = default 64) — every CTA spins on peer flags, so
+ *   max_ctas: upper bound on the CTAs used (<= SM count; 0 = one per SM, measured best at N = 8) — every CTA spins on peer flags, so
  *   the grid must be co-resident with whatever else runs concurrently. */
 int tt_dp_reduce_adam(void* const* segments, int world, int rank, size_t n_param, const float* grad,
                       float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,

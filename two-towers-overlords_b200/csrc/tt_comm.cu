@@ -318,7 +318,7 @@ extern "C" int tt_dp_reduce_adam(void* const* segments, int world, int rank, siz
   const DpLayout L = dp_layout(n_param, world);
   // every CTA spins on peer flags, so the grid must be co-resident: never more than one CTA per SM
   long long ctas = (long long)((L.S / 4 + kDpThreads - 1) / kDpThreads);
-  const int cap = max_ctas > 0 ? (max_ctas < sm_count() ? max_ctas : sm_count()) : 64;
+  const int cap = max_ctas > 0 ? (max_ctas < sm_count() ? max_ctas : sm_count()) : sm_count();
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   TT_CUDA(launch_pdl(dp_rs_adam_ag_kernel, dim3((unsigned)ctas), dim3(kDpThreads), 0, as_stream(stream), p));

@@ -448,6 +448,12 @@ int launch_gemm(const GemmDesc* d, int ngroups, int n_pairs, int splits, float* 
 
 int choose_splits(int tiles, int K) {
   const int kb = (K + BK - 1) / BK;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("TT_GEMM_SPLITS");  // tuning hook
+    env = e ? atoi(e) : 0;
+  }
+  if (env >= 2) return min(env, max(kb, 2));
   int s = (2 * sm_count() + tiles - 1) / tiles;
   s = min(s, kb);
   s = min(s, 32);
