@@ -5,9 +5,11 @@ backend/training.py: `clear_gpu_memory`, `train_epoch`, `train_epoch_optimized`,
 runs on top unchanged.
 
 Additions (the B200 path proper):
-  * FusedTrainer      one tt_triplet_step (pooled gather -> both tower MLPs -> loss -> all gradients) + one
-                      fused Adam launch per step, captured in a CUDA graph; data-parallel with ONE NCCL
-                      all-reduce of the flat gradient buffer (+ the loss in its last slot) per step.
+  * FusedTrainer      one tt_triplet_step (pooled gather -> both tower MLPs -> loss -> all gradients) + Adam per
+                      step, captured as one CUDA graph whose branches run in parallel (the next step's pooled
+                      gather beside this step's tensor-core chain); data-parallel with ONE fused kernel per step
+                      (reduce-scatter over NVLink peer memory -> Adam -> all-gather; NCCL all-reduce + Adam as the
+                      baseline); batches assembled on the device (train_epoch_device); checkpoint / resume.
   * evaluate_model    scores every query against the candidate documents with the corpus-scan / candidate
                       kernels and computes NDCG@k on the device; only tie cases that the closed form cannot
                       express fall back to the exact tie-averaged formula.
@@ -114,12 +116,15 @@ def train_epoch_optimized(model, dataloader, criterion, optimizer, device, scale
 # fused B200 trainer
 # --------------------------------------------------------------------------------------------------
 class FusedTrainer:
-    """Whole training step (training.py:37-51) as: H2D token copy -> tt_triplet_step -> [NCCL all-reduce]
-    -> tt_adam_step_dev, on static buffers so the device part replays as one CUDA graph.
+    """Whole training step (training.py:37-51) as: tokens into a static slot (one packed H2D copy or the device
+    feeder) -> tt_triplet_step -> tt_adam_step_dev (one GPU) / tt_dp_reduce_adam (data parallel, peer memory) /
+    NCCL all-reduce + Adam (baseline), on static buffers so the device part replays as one CUDA graph.
 
+    `step(slot, next_slot)` software-pipelines consecutive steps: the pooled gather of `next_slot` runs beside
+    the rest of `slot` (it reads tokens and the frozen tables only, so this is still exact synchronous SGD).
     The 8 projection tensors are re-pointed at views of one flat fp32 buffer, so the model's
     `state_dict()` / `parameters()` always see the trained values; gradients live in a second flat buffer
-    whose last element carries the loss (one all-reduce covers both)."""
+    whose last element carries the loss (one exchange covers both)."""
 
     def __init__(self, model: TwoTowersModel, margin: float, lr: float, batch_size: int, Lq: int = 32, Ld: int = 256,
                  precision: Optional[str] = None, world_size: int = 1, rank: int = 0, use_graph: bool = True,
