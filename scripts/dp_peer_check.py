@@ -15,7 +15,17 @@ dev = torch.device("cuda", local)
 os.environ.setdefault("NCCL_DEBUG", "WARN")
 dist.init_process_group("nccl", device_id=dev)
 
-from oracle import two_towers_oracle as O  # noqa: E402  (test infrastructure: synthetic batches only)
+
+
+def synth_batch(B, Lq, Ld, seed, vocab):
+    """Shape-U synthetic triplet tokens: (q_ids, q_mask, p_ids, p_mask, n_ids, n_mask), negatives = rolled positives."""
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randint(999, vocab, (B, Lq), generator=g, dtype=torch.int64)
+    p = torch.randint(999, vocab, (B, Ld), generator=g, dtype=torch.int64)
+    n = torch.roll(p, 1 + seed % (B - 1), 0)
+    return tuple(t for ids in (q, p, n) for t in (ids, torch.ones_like(ids)))
+
+
 from two_towers_overlords_b200 import TwoTowersModel  # noqa: E402
 from two_towers_overlords_b200.training import FusedTrainer  # noqa: E402
 
@@ -27,14 +37,14 @@ for exchange in ("nccl", "peer", "peer-pipelined"):
     tr = FusedTrainer(model, 0.3, 1e-3, B, Lq, Ld, precision="bf16x3", world_size=world, rank=rank,
                       ids_dtype=torch.int64, mask_dtype=torch.int64, exchange=exchange.split("-")[0], token_slots=2)
     losses = []
-    batches = [O.synth_triplet_batch(B, Lq, Ld, "U", seed=100 * i + rank, vocab=V) for i in range(STEPS)]
-    tr.load_packed(tr.pack_host_tokens(batches[0].astuple(), pin=False), 0)
+    batches = [synth_batch(B, Lq, Ld, 100 * i + rank, V) for i in range(STEPS)]
+    tr.load_packed(tr.pack_host_tokens(batches[0], pin=False), 0)
     for i in range(STEPS):
         nslot = None
         if i + 1 < STEPS:
             if exchange == "peer-pipelined":
                 nslot = (i + 1) % 2
-            tr.load_packed(tr.pack_host_tokens(batches[i + 1].astuple(), pin=False), (i + 1) % 2)
+            tr.load_packed(tr.pack_host_tokens(batches[i + 1], pin=False), (i + 1) % 2)
         tr.step(i % 2, nslot)
         losses.append(float(tr.loss_view[0].item()))
     torch.cuda.synchronize()
