@@ -14,6 +14,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """Make sure libtt_b200.so matches the sources (incremental: a no-op when it is up to date).  The product never
+    builds itself at import time — a missing library is a loud error there — but a test run should not depend on
+    somebody having called __graft_entry__.build() first."""
+    import importlib.util
+    import shutil
+
+    path = os.path.join(ROOT, "two-towers-overlords_b200", "csrc", "build.py")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not (os.path.exists(nvcc) or shutil.which("nvcc")):
+        return
+    spec = importlib.util.spec_from_file_location("tt_b200_build", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+
+
 def pytest_collection_modifyitems(config, items):
     """GPU-marked tests are skipped automatically where no CUDA device exists."""
     import torch
