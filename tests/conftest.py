@@ -28,7 +28,12 @@ def pytest_sessionstart(session):
     spec = importlib.util.spec_from_file_location("tt_b200_build", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    mod.build()
+    try:
+        mod.build()
+    except Exception as e:  # noqa: BLE001  (an existing library still gets tested; a missing one fails loudly later)
+        if not os.path.exists(mod.LIB):
+            raise
+        print(f"warning: could not refresh {mod.LIB}: {e}")
 
 
 def pytest_collection_modifyitems(config, items):
