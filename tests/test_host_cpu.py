@@ -291,3 +291,27 @@ def test_reference_arm_prints_one_json_line_on_cpu():
     assert d["impl"] == "reference" and d["metric"] == "train_triplets_per_sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_synthetic_token_sets_follow_the_stated_shape():
+    """bench.py's synthetic inputs: shape U (full-length rows, ids in [999, 30522)), negatives = the positives of
+    another item of the batch (no fixed point), same bytes for the same seed."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tt_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = bench.token_sets(2, 64, 7, torch.uint16, torch.uint8, pin=False)
+    b = bench.token_sets(2, 64, 7, torch.uint16, torch.uint8, pin=False)
+    for sa, sb in zip(a, b):
+        q, qm, p, pm, n, nm = sa
+        assert tuple(q.shape) == (64, bench.LQ) and tuple(p.shape) == (64, bench.LD) and q.dtype == torch.uint16
+        assert int(q.to(torch.int64).min()) >= 999 and int(p.to(torch.int64).max()) < bench.VOCAB
+        assert bool(qm.all()) and bool(pm.all()) and bool(nm.all())
+        pi, ni = p.to(torch.int64), n.to(torch.int64)
+        assert not any(torch.equal(pi[i], ni[i]) for i in range(64))          # never its own positive
+        assert all(any(torch.equal(ni[i], pi[j]) for j in range(64)) for i in range(0, 64, 9))  # an in-batch positive
+        assert all(torch.equal(x, y) for x, y in zip(sa, sb))
+    cfg = bench.workload_config(8, "bf16x3", "f32")
+    assert cfg["global_batch"] == 8 * bench.B_PER_GPU and cfg["parallelism"] == "dp8" and "workload" in cfg
