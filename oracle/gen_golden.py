@@ -212,6 +212,67 @@ def main():
             cases[f"ndcg{k}_{c}"] = np.float64(ndcg_score(rel.reshape(1, -1), score.reshape(1, -1), k=k))
     cases["n_cases"] = np.int64(24)
     np.savez_compressed(os.path.join(OUT, "ndcg_sklearn.npz"), **cases)
+
+    # ---------------------------------------------------------------- 6. train_epoch at P = 64 (the smallest
+    # projection the split-bf16 tensor-core path accepts), own rng so sections 1-5 keep their draws
+    rng6 = np.random.default_rng(6006)
+    torch.manual_seed(78)
+    P, margin, lr = 64, 0.3, 1e-3
+    m = ref_model.TwoTowersModel(projection_dim=P)
+    crit = ref_model.TripletLoss(margin=margin)
+    opt = torch.optim.Adam(m.parameters(), lr=lr)
+    init = _params(m)
+    batches = []
+    for _ in range(3):
+        B = 16
+        batches.append(([f"q:{i}" for i in rng6.integers(0, 64, B)],
+                        [f"d:{i}" for i in rng6.integers(0, 160, B)],
+                        [f"d:{i}" for i in rng6.integers(0, 160, B)]))
+    avg = ref_training.train_epoch(m, batches, crit, opt, log_wandb=False)
+    out = {"init__" + k: v for k, v in init.items()}
+    out.update({"final__" + k: v for k, v in _params(m).items()})
+    for bi, (qs, ps, ns) in enumerate(batches):
+        for nm, texts in (("q", qs), ("p", ps), ("n", ns)):
+            ids, msk = _tok(texts)
+            out[f"b{bi}_{nm}_ids"], out[f"b{bi}_{nm}_mask"] = ids, msk
+    out.update(avg_loss=np.float64(avg), margin=np.float32(margin), lr=np.float64(lr))
+    np.savez_compressed(os.path.join(OUT, "train_epoch_p64.npz"), **out)
+
+    # ---------------------------------------------------------------- 7. train_epoch_optimized (training.py:66-133):
+    # the reference's own loop (accumulation cadence, loss / accumulation_steps, GradScaler scale -> step -> update ->
+    # zero_grad) on CPU.  autocast is replaced by a null context so the arithmetic stays fp32 (the CUDA path here
+    # computes in fp32 / split-bf16 regardless of autocast); GradScaler("cpu") is the real one (power-of-two scale).
+    import contextlib
+
+    rng7 = np.random.default_rng(7007)
+    torch.manual_seed(79)
+    P, margin, lr, accum = 64, 0.3, 1e-3, 2
+    m = ref_model.TwoTowersModel(projection_dim=P)
+    crit = ref_model.TripletLoss(margin=margin)
+    opt = torch.optim.Adam(m.parameters(), lr=lr)
+    init = _params(m)
+    batches = []
+    for _ in range(5):  # odd count: the trailing batch is accumulated but never stepped (reference behaviour)
+        B = 16
+        batches.append(([f"q:{i}" for i in rng7.integers(0, 64, B)],
+                        [f"d:{i}" for i in rng7.integers(0, 160, B)],
+                        [f"d:{i}" for i in rng7.integers(0, 160, B)]))
+    ref_training.autocast = lambda *a, **k: contextlib.nullcontext()
+    scaler = torch.amp.GradScaler("cpu")
+    avg = ref_training.train_epoch_optimized(m, batches, crit, opt, torch.device("cpu"), scaler,
+                                             accumulation_steps=accum, log_wandb=False)
+    out = {"init__" + k: v for k, v in init.items()}
+    out.update({"final__" + k: v for k, v in _params(m).items()})
+    for name, prm in m.named_parameters():  # gradient left behind by the unstepped 5th batch (scaled by the scaler)
+        if prm.grad is not None:
+            out["leftover_grad__" + name.replace(".", "__")] = (prm.grad / scaler.get_scale()).numpy().copy()
+    for bi, (qs, ps, ns) in enumerate(batches):
+        for nm, texts in (("q", qs), ("p", ps), ("n", ns)):
+            ids, msk = _tok(texts)
+            out[f"b{bi}_{nm}_ids"], out[f"b{bi}_{nm}_mask"] = ids, msk
+    out.update(avg_loss=np.float64(avg), margin=np.float32(margin), lr=np.float64(lr), accum=np.int64(accum),
+               n_batches=np.int64(len(batches)))
+    np.savez_compressed(os.path.join(OUT, "train_epoch_optimized.npz"), **out)
     print("golden vectors written to", OUT)
 
 

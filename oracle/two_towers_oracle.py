@@ -124,6 +124,28 @@ def train_step(model: OracleTwoTowers, optimizer: torch.optim.Optimizer, batch, 
     return loss.item()
 
 
+def train_epoch_accum(model: OracleTwoTowers, optimizer: torch.optim.Optimizer, batches, margin: float,
+                      accumulation_steps: int = 2) -> float:
+    """backend/training.py:81-133 (train_epoch_optimized) in fp32: loss / accumulation_steps, gradients accumulate
+    across batches, optimiser step + zero_grad every `accumulation_steps` batches (a trailing partial group is
+    accumulated but never stepped), returns the mean of the unscaled per-batch losses.  autocast and GradScaler
+    are left out: the scaler multiplies by a power of two and divides it back (exact in fp32), and the CUDA path
+    this oracle checks computes in fp32 / split-bf16 regardless of autocast."""
+    total, nb = 0.0, 0
+    for idx, (q_ids, q_mask, p_ids, p_mask, n_ids, n_mask) in enumerate(batches):
+        q = model.encode_queries(q_ids, q_mask)
+        p = model.encode_documents(p_ids, p_mask)
+        n = model.encode_documents(n_ids, n_mask)
+        loss = triplet_loss(q, p, n, margin) / accumulation_steps
+        loss.backward()
+        if (idx + 1) % accumulation_steps == 0:
+            optimizer.step()
+            optimizer.zero_grad()
+        total += loss.item() * accumulation_steps
+        nb += 1
+    return total / nb
+
+
 # ----------------------------------------------------------------------------------------------
 # evaluation
 # ----------------------------------------------------------------------------------------------

@@ -179,7 +179,7 @@ _GLOO_WORKER = r"""
 import os, sys, torch, numpy as np
 import torch.distributed as dist
 sys.path.insert(0, os.environ["TT_ROOT"])
-from two_towers_overlords_b200 import data, retrieval
+from two_towers_overlords_b200 import data, retrieval, training
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["TT_PORT"], rank=int(os.environ["RANK"]), world_size=2)
 rank = dist.get_rank()
 # 1. every rank draws the same global batches and owns a disjoint contiguous slice
@@ -200,6 +200,34 @@ s = torch.full((4, 10), float(rank)); i = torch.arange(lo, lo + 40).view(4, 10)
 ps, pi = retrieval.all_gather_lists(s, i, 2)
 assert ps.shape == (2, 4, 10) and pi.dtype == torch.int64
 assert ps[1].eq(1).all() and int(pi[1, 0, 0]) == retrieval.shard_bounds(1001, 2, 1)[0]
+# 4. evaluate_model under data parallelism: rank 0's sampling plan becomes everybody's (the ranks' `random` states
+#    differ), and every rank owns a contiguous shard of the document universe
+import random
+random.seed(100 + rank)
+val = data.MSMarcoDataset("validation", max_samples=300, synthetic=True)
+box = [training._eval_plan(val, 60, 8, 20, say=lambda *a, **k: None) if rank == 0 else None]
+dist.broadcast_object_list(box, src=0)
+plan = box[0]
+sig = repr((plan["queries"], plan["rel_docs"], plan["cand_docs"]))
+sigs = [None, None]
+dist.all_gather_object(sigs, sig)
+assert sigs[0] == sigs[1] and len(plan["queries"]) == 8 and all(len(c) >= 2 for c in plan["cand_docs"])
+universe = list(dict.fromkeys(d for r in plan["rel_docs"] for d in r))
+lo, hi = retrieval.shard_bounds(len(universe), 2, rank)
+spans = [None, None]
+dist.all_gather_object(spans, (lo, hi))
+assert spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == len(universe)
+# 5. shard embeddings of different heights reassemble in rank order (validation pools gather the shards)
+rows = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3)
+allrows = training._gather_rows(rows, 2)
+assert allrows.shape == (len(universe), 3) and torch.equal(allrows[:, 0], torch.arange(len(universe), dtype=torch.float32))
+# 6. mixed-bank handles resolve per bank (train + validation passages in one call)
+tok = val.tokenizer()
+tok.add(ds.tokenizer())
+mixed = tok([val.docs[0], ds.docs[0], val.docs[1]])
+assert mixed["input_ids"].shape[0] == 3
+assert torch.equal(mixed["input_ids"][1, : int(mixed["attention_mask"][1].sum())].to(torch.int64),
+                   torch.from_numpy(ds.doc_bank.tokens(0)).to(torch.int64))
 dist.destroy_process_group()
 print("ok", rank)
 """

@@ -75,6 +75,45 @@ def test_train_epoch_matches_reference(golden_dir):
                 assert torch.equal(got, ref), (tower, idx, kind)
 
 
+def test_train_epoch_p64_matches_reference(golden_dir):
+    """Same pin at P = 64, the fixture the split-bf16 fused step is checked against on the GPU."""
+    g = _load(golden_dir, "train_epoch_p64.npz")
+    m = _oracle_model_from(g, 64, prefix="init__")
+    opt = torch.optim.Adam(m.parameters(), lr=float(g["lr"]))
+    losses = []
+    for b in range(3):
+        batch = tuple(_t(g[f"b{b}_{nm}_{k}"]) for nm in ("q", "p", "n") for k in ("ids", "mask"))
+        losses.append(O.train_step(m, opt, batch, float(g["margin"])))
+    assert np.mean(losses) == pytest.approx(float(g["avg_loss"]), rel=1e-7)
+    for tower in ("query_tower", "document_tower"):
+        for idx in (0, 2):
+            for kind in ("weight", "bias"):
+                ref = _t(g[f"final__{tower}__projection__{idx}__{kind}"])
+                got = getattr(getattr(m, tower).projection[idx], kind).detach()
+                assert torch.equal(got, ref), (tower, idx, kind)
+
+
+def test_train_epoch_accum_matches_reference_train_epoch_optimized(golden_dir):
+    """oracle.train_epoch_accum == the reference's own train_epoch_optimized (fp32 autocast stand-in, real
+    GradScaler): losses, weights after 2 optimiser steps over 5 batches, and the gradient the unstepped trailing
+    batch leaves behind."""
+    g = _load(golden_dir, "train_epoch_optimized.npz")
+    m = _oracle_model_from(g, 64, prefix="init__")
+    opt = torch.optim.Adam(m.parameters(), lr=float(g["lr"]))
+    batches = [tuple(_t(g[f"b{b}_{nm}_{k}"]) for nm in ("q", "p", "n") for k in ("ids", "mask"))
+               for b in range(int(g["n_batches"]))]
+    avg = O.train_epoch_accum(m, opt, batches, float(g["margin"]), int(g["accum"]))
+    assert avg == pytest.approx(float(g["avg_loss"]), rel=1e-7)
+    for tower in ("query_tower", "document_tower"):
+        for idx in (0, 2):
+            for kind in ("weight", "bias"):
+                ref = _t(g[f"final__{tower}__projection__{idx}__{kind}"])
+                prm = getattr(getattr(m, tower).projection[idx], kind)
+                assert torch.equal(prm.detach(), ref), (tower, idx, kind)
+                left = _t(g[f"leftover_grad__{tower}__projection__{idx}__{kind}"])
+                assert torch.allclose(prm.grad, left, rtol=1e-6, atol=1e-12), (tower, idx, kind)
+
+
 def test_ndcg_matches_sklearn_golden(golden_dir):
     g = _load(golden_dir, "ndcg_sklearn.npz")
     for c in range(int(g["n_cases"])):

@@ -14,6 +14,7 @@
 // Flags only ever grow (epoch counter), nothing is reset, and the landing zone needs no double buffering: a peer
 // can only start pushing step e+1 after it has seen MY parameter flag of step e, which I raise after my last read
 // of the landing zone.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tt_common.cuh"
@@ -24,6 +25,18 @@ namespace {
 constexpr int kMaxWorld = 8;
 constexpr int kDpThreads = 256;
 constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s: a lost peer becomes an error, not a hung GPU
+
+// TT_DP_TIMEOUT_MS overrides the spin timeout of the exchange / barrier kernels (rank-local work such as an
+// evaluation on rank 0 must finish inside it, or be fenced by a host barrier first)
+unsigned long long spin_timeout_ns() {
+  static unsigned long long v = 0;
+  if (!v) {
+    const char* e = getenv("TT_DP_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 0;
+    v = ms > 0 ? (unsigned long long)ms * 1000000ull : kSpinTimeoutNs;
+  }
+  return v;
+}
 
 struct DpLayout {
   size_t S;          // slice length in floats (multiple of 4)
@@ -53,6 +66,7 @@ struct DpParams {
   double* state;      // {t, beta1^t, beta2^t, -}
   unsigned* ctl;      // {epoch, ticket1, ticket2, error, then 4 x u64 diagnostics: ns until all gradient flags,
                       //  ns from there to the end of the kernel, calls, ns of the own push}
+  unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -69,19 +83,24 @@ __device__ __forceinline__ unsigned long long globaltimer() {
   return t;
 }
 // waits until *flag >= epoch (wrap-safe); false on timeout
-__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch) {
+__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, unsigned long long timeout_ns) {
   if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return true;
   const unsigned long long t0 = globaltimer();
   for (;;) {
     for (int i = 0; i < 64; ++i)
       if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return true;
-    if (globaltimer() - t0 > kSpinTimeoutNs) return false;
+    if (globaltimer() - t0 > timeout_ns) return false;
   }
 }
 
 __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_constant__ DpParams p) {
   pdl_wait();
   pdl_launch();
+  // Sticky error: once a peer has timed out (ctl[3] != 0) the protocol state (tickets, epoch, the peers' flags) is
+  // no longer consistent, so every later launch is a no-op until the host has seen the error (DpExchange.check()
+  // raises) — no update is ever applied on half-exchanged gradients.  The value is stable for the whole kernel only
+  // when it is already set at launch; a timeout inside THIS launch makes the failing CTA return below.
+  if (*reinterpret_cast<volatile unsigned*>(&p.ctl[3]) != 0u) return;
   const DpLayout L = dp_layout(p.n, p.world);
   const int tid = threadIdx.x, W = p.world, me = p.rank;
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&p.ctl[0]) + 1u;
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_
     }
   }
   // ---- phase 2: reduce my slice in rank order, Adam, broadcast the new parameters ----------------------------------
-  if (tid < W && !wait_flag(my_flags + tid, epoch)) s_fail = 1;
+  if (tid < W && !wait_flag(my_flags + tid, epoch, p.timeout_ns)) s_fail = 1;
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0) t_flags = globaltimer();
   if (s_fail) {
@@ -192,7 +211,7 @@ __global__ void __launch_bounds__(kDpThreads) dp_rs_adam_ag_kernel(const __grid_
   }
   __syncthreads();
   // ---- phase 3: the last CTA holds the kernel open until every rank's parameter slice has landed here ----------------
-  if (s_last && tid < W && !wait_flag(my_flags + W + tid, epoch)) p.ctl[3] = 1;
+  if (s_last && tid < W && !wait_flag(my_flags + W + tid, epoch, p.timeout_ns)) p.ctl[3] = 1;
   if (blockIdx.x == 0 && tid == 0) {  // diagnostics (CTA 0's view; it is not necessarily the last CTA)
     unsigned long long* d = reinterpret_cast<unsigned long long*>(p.ctl + 4);
     d[0] += t_flags - t_start;
@@ -207,6 +226,7 @@ struct BarrierParams {
   unsigned* flags[kMaxWorld];
   int world, rank;
   unsigned* ctl;  // {epoch, -, -, error}
+  unsigned long long timeout_ns;
 };
 
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
   __threadfence_system();
   if (tid < p.world) {
     st_release_sys(p.flags[tid] + p.rank, epoch);
-    if (!wait_flag(p.flags[p.rank] + tid, epoch)) p.ctl[3] = 1;
+    if (!wait_flag(p.flags[p.rank] + tid, epoch, p.timeout_ns)) p.ctl[3] = 1;
   }
   __syncwarp();
   if (tid == 0) p.ctl[0] = epoch;
@@ -315,6 +335,7 @@ extern "C" int tt_dp_reduce_adam(void* const* segments, int world, int rank, siz
   }
   p.world = world; p.rank = rank; p.n = n_param; p.grad = grad; p.m = exp_avg; p.v = exp_avg_sq;
   p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.state = state; p.ctl = ctl;
+  p.timeout_ns = spin_timeout_ns();
   const DpLayout L = dp_layout(n_param, world);
   // every CTA spins on peer flags, so the grid must be co-resident: never more than one CTA per SM
   long long ctas = (long long)((L.S / 4 + kDpThreads - 1) / kDpThreads);
@@ -334,6 +355,7 @@ extern "C" int tt_peer_barrier(void* const* flags, int world, int rank, unsigned
     p.flags[r] = reinterpret_cast<unsigned*>(flags[r]);
   }
   p.world = world; p.rank = rank; p.ctl = ctl;
+  p.timeout_ns = spin_timeout_ns();
   peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(p);
   TT_LAUNCH_CHECK();
   return 0;

@@ -97,18 +97,43 @@ class TokenBank:
 
 
 class TokenBankTokenizer:
-    """Resolves text handles against token banks; same call/return shape as the HF tokenizer."""
+    """Resolves text handles ("<bank prefix>:<index>") against token banks; same call/return shape as the HF
+    tokenizer.  A batch may mix handles of several banks (e.g. passages of the train and the test split)."""
 
     def __init__(self, *banks: TokenBank):
-        self.banks = {b.prefix: b for b in banks}
+        self.banks: dict[str, TokenBank] = {}
+        for b in banks:
+            self.add_bank(b)
+
+    def add_bank(self, bank: TokenBank):
+        have = self.banks.get(bank.prefix)
+        if have is not None and have is not bank:
+            raise ValueError(f"two different token banks share the handle prefix {bank.prefix!r}")
+        self.banks[bank.prefix] = bank
+
+    def add(self, other: "TokenBankTokenizer"):
+        for b in other.banks.values():
+            self.add_bank(b)
 
     def __call__(self, texts, padding=True, truncation=True, return_tensors="pt", max_length=512):
-        prefix = texts[0].split(":", 1)[0]
-        bank = self.banks[prefix]
+        prefixes = [t.split(":", 1)[0] for t in texts]
         idx = np.fromiter((int(t.split(":", 1)[1]) for t in texts), dtype=np.int64, count=len(texts))
-        tb = bank.batch(idx, max_length=max_length)
-        return {"input_ids": tb.input_ids, "token_type_ids": torch.zeros_like(tb.input_ids),
-                "attention_mask": tb.attention_mask}
+        if all(p == prefixes[0] for p in prefixes):
+            tb = self.banks[prefixes[0]].batch(idx, max_length=max_length)
+            ids, mask = tb.input_ids, tb.attention_mask
+        else:  # mixed banks: resolve each group, then pad to the batch max like padding=True does
+            groups: dict[str, list[int]] = {}
+            for pos, p in enumerate(prefixes):
+                groups.setdefault(p, []).append(pos)
+            parts = {p: self.banks[p].batch(idx[rows], max_length=max_length) for p, rows in groups.items()}
+            L = max(tb.input_ids.shape[1] for tb in parts.values())
+            ids = torch.zeros(len(texts), L, dtype=torch.int64)
+            mask = torch.zeros(len(texts), L, dtype=torch.int64)
+            for p, rows in groups.items():
+                tb = parts[p]
+                ids[rows, : tb.input_ids.shape[1]] = tb.input_ids.to(torch.int64)
+                mask[rows, : tb.input_ids.shape[1]] = tb.attention_mask.to(torch.int64)
+        return {"input_ids": ids, "token_type_ids": torch.zeros_like(ids), "attention_mask": mask}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -172,8 +197,8 @@ class MSMarcoDataset(torch.utils.data.Dataset):
             per = per[:-1]
             per[-1] += n_pairs - int(per.sum())
         n_docs = int(per.sum())
-        self.query_bank = TokenBank.synthetic(f"{split[0]}q", len(per), "query", seed + 1)
-        self.doc_bank = TokenBank.synthetic(f"{split[0]}d", n_docs, "doc", seed + 2)
+        self.query_bank = TokenBank.synthetic(f"{split}.q", len(per), "query", seed + 1)
+        self.doc_bank = TokenBank.synthetic(f"{split}.d", n_docs, "doc", seed + 2)
         d = 0
         for qi, c in enumerate(per):
             for _ in range(int(c)):

@@ -257,6 +257,13 @@ class TripletStep:
         self._keep.append(tokens)
         return len(self.slots) - 1
 
+    def pooled_rows(self) -> torch.Tensor:
+        """xhat [3B,H] fp32 of the last run, rows q | p | n: the first carve of the step workspace
+        (carve_step_ws in csrc/tt_api.cu).  Read-only view for the parity tests."""
+        B, _, _, H = self.shape[:4]
+        assert self.ws.data_ptr() % 256 == 0
+        return self.ws[: 3 * B * H * 4].view(torch.float32).view(3 * B, H)
+
     def run(self, slot: int = 0, phases: int = 0):
         """phases: 0 = whole step, 1 = pooled gather only (TT_STEP_FRONT), 2 = the rest (TT_STEP_BACK)."""
         a = self.slots[slot]
@@ -281,6 +288,8 @@ def l2_normalize_rows(x: torch.Tensor, eps: float = 1e-8, want_bf16: bool = Fals
     x = x.contiguous().float()
     y = torch.empty_like(x)
     yb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    if x.shape[0] == 0:  # an empty shard (more ranks than documents)
+        return (y, yb) if want_bf16 else y
     N.check(N.load().tt_l2_normalize_rows(N.ptr(x), x.shape[0], x.shape[1], eps, N.ptr(y), N.ptr(yb), N.stream()),
             "tt_l2_normalize_rows")
     return (y, yb) if want_bf16 else y

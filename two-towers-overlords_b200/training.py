@@ -26,12 +26,13 @@ import torch
 from torch import GradScaler, autocast
 
 try:
-    from . import comm, ops
+    from . import comm, ops, retrieval
     from .data import DeviceTripletFeeder, MSMarcoDataset, TokenTripletLoader, TripletDataLoader
     from .model import TokenBatch, TripletLoss, TwoTowersModel
 except ImportError:
     import comm
     import ops
+    import retrieval
     from data import DeviceTripletFeeder, MSMarcoDataset, TokenTripletLoader, TripletDataLoader
     from model import TokenBatch, TripletLoss, TwoTowersModel
 
@@ -178,6 +179,9 @@ class FusedTrainer:
                 self.p_views.append(view)
                 self.g_views.append(self.flat_g[off: off + n].view_as(p))
                 off += n
+        # data-parallel replicas must start from the same weights: only gradients are exchanged afterwards (the peer
+        # exchange overwrites parameters slice by slice AFTER the first gradients were taken on the local ones)
+        self._sync_initial_state()
         # where the step's GLOBAL loss can be read: slot n of the flat gradient (summed in place by NCCL), or slot n
         # of the peer segment (written by the exchange kernel)
         self.loss_view = self.xchg.loss if self.xchg is not None else self.flat_g[self.n_param:]
@@ -222,6 +226,7 @@ class FusedTrainer:
         self.use_graph = use_graph
         self.graphs = {}       # (slot, next_slot, parity) -> CUDAGraph
         self.graph_opt = None  # NCCL mode: Adam after the all-reduce
+        self.graph_captures = 0  # bench.py asserts that none happens inside a timed region
         self.side = torch.cuda.Stream(device=dev)
         # graphs are captured on a high-priority stream: the latency-bound chain then takes SM slots ahead of the
         # bandwidth-bound pooled gather running beside it (measured 291 -> 268 us per step)
@@ -231,6 +236,45 @@ class FusedTrainer:
         self._warm = False
         self.steps_done = 0
         self.kernel_launches_per_step = None
+
+    # -- data-parallel hygiene ---------------------------------------------------------------------
+    def _dist_ready(self) -> bool:
+        import torch.distributed as dist
+
+        return self.world > 1 and dist.is_available() and dist.is_initialized()
+
+    def _sync_initial_state(self):
+        """Rank 0's projection weights (and Adam step count) become everybody's.  Collective when world_size > 1 and a
+        process group exists (virtual-rank tests run several ranks in one process without one)."""
+        if not self._dist_ready():
+            return
+        import torch.distributed as dist
+
+        tmp = self.flat_p.clone()  # the peer segment is library-owned memory: broadcast through a torch tensor
+        dist.broadcast(tmp, src=0, group=self.pg)
+        if not torch.equal(tmp, self.flat_p):
+            if self.rank != 0:
+                print(f"[rank {self.rank}] FusedTrainer: initial projection weights differed from rank 0's; "
+                      "taking rank 0's")
+            self.flat_p.copy_(tmp)
+        st = self.xchg.state if self.xchg is not None else self.adam_state
+        dist.broadcast(st, src=0, group=self.pg)
+        torch.cuda.synchronize()
+
+    def sync_ranks(self):
+        """Host barrier: call after rank-local work (evaluation, checkpoint writes, graph capture) and before the next
+        exchanged step, so that no rank spins in the exchange kernel past its timeout waiting for a busy peer."""
+        torch.cuda.synchronize()
+        if self._dist_ready():
+            import torch.distributed as dist
+
+            dist.barrier(group=self.pg)
+
+    def check(self):
+        """Raises if the peer exchange reported an error (a rank that never answered).  Host sync; called wherever the
+        loss is read on the host and at the end of every epoch."""
+        if self.xchg is not None:
+            self.xchg.check()
 
     # -- pieces ------------------------------------------------------------------------------------
     def load_tokens(self, q: TokenBatch, p: TokenBatch, n: TokenBatch, slot: int = 0):
@@ -314,6 +358,7 @@ class FusedTrainer:
             with torch.cuda.graph(g, stream=self.cap_stream):
                 self._pipelined(slot, next_slot, parity)
             self.graphs[key] = g
+            self.graph_captures += 1
             self.kernel_launches_per_step = lib.tt_launch_count() - n0
             if self.world > 1 and self.xchg is None:
                 if self.graph_opt is None:
@@ -335,6 +380,7 @@ class FusedTrainer:
             nxt = (s_ + 1) % n
             for parity in ((s_ & 1,) if n % 2 == 0 else (0, 1)):
                 self._graph(s_, nxt, parity)
+        self.sync_ranks()  # capture time differs per rank: line the ranks up before the first exchanged step
 
     def step(self, slot: int = 0, next_slot: Optional[int] = None) -> torch.Tensor:
         """One optimiser step on the tokens in the static buffers of `slot`; returns the (global) loss as a device
@@ -345,9 +391,12 @@ class FusedTrainer:
         if self.train_table:
             next_slot = None  # a trainable table changes between steps: its gather cannot run ahead of the update
         lib = ops.N.load()
-        parity = self._parity
         if self._primed != slot:  # pipeline start (or a schedule change): this step's gather has not run yet
-            self._fwd_bwd(slot, 1, parity)
+            # nothing is primed, so the workspace is free to choose: make it a function of the slot, which is what
+            # prepare() captured for an even slot count (a restart must never land on an uncaptured graph key)
+            self._parity = slot & 1
+            self._fwd_bwd(slot, 1, self._parity)
+        parity = self._parity
         if self.use_graph:
             self._graph(slot, next_slot, parity).replay()
         else:
@@ -388,9 +437,13 @@ class FusedTrainer:
             if i + 1 < steps and n_slots < 2:
                 feeder.assemble(self, 0, i + 1)
             if log_every and (i + 1) % log_every == 0:
-                print(f"Batch {i + 1}, Loss: {loss.item():.4f}")
+                if self.rank == 0:
+                    print(f"Batch {i + 1}, Loss: {loss.item():.4f}")
+                self.check()
         feeder.check()
-        return float(total.item()) / steps
+        avg = float(total.item()) / steps
+        self.check()
+        return avg
 
     # -- checkpoint / resume (main.py:142-152 saves `model.state_dict()`; this adds the optimiser so a run can resume) --
     def _slice_bounds(self):
@@ -424,11 +477,13 @@ class FusedTrainer:
             self.adam_state.copy_(sd["adam_state"])
         self.steps_done = int(sd.get("steps_done", 0))
         self._primed = None
+        self._sync_initial_state()
 
     def save_checkpoint(self, path: str):
         sd = self.state_dict()
         if self.rank == 0:
             torch.save(sd, path)
+        self.sync_ranks()  # rank 0 was busy writing: nobody enters the next exchange before it is back
 
     def load_checkpoint(self, path: str):
         self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
@@ -473,13 +528,17 @@ class FusedTrainer:
             total += loss.double()
             nb += 1
             if log_every and nb % log_every == 0:
-                print(f"Batch {nb}, Loss: {loss.item():.4f}")
+                if self.rank == 0:
+                    print(f"Batch {nb}, Loss: {loss.item():.4f}")
+                self.check()
             if nxt is not None and nslot is None:
                 self.load_tokens(*nxt, slot=slot)
             else:
                 slot = nslot if nslot is not None else slot
             cur = nxt
-        return float(total.item()) / nb
+        avg = float(total.item()) / nb
+        self.check()
+        return avg
 
 
 # --------------------------------------------------------------------------------------------------
@@ -528,6 +587,68 @@ def _ndcg_from_lists(top_s: np.ndarray, top_i: np.ndarray, relevant: set, n_rel_
     return 0.0 if idcg == 0 else dcg / idcg
 
 
+def _dist_info():
+    """(world_size, rank) of the default process group, (1, 0) without one."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def _eval_plan(dataset, sample_size: int, min_query_groups: int, candidate_pool_size: int, say=print) -> dict:
+    """Host part of evaluate_model (training.py:184-279): sample + group by query_id until enough unique queries
+    (same `random` call sequence as the reference), keep the queries with most relevant documents, and build the
+    per-query candidate pools.  Pure Python on strings — under data parallelism rank 0 runs it and broadcasts the
+    result, so that every rank scores the same queries against the same pools."""
+    query_groups: dict[int, dict] = {}
+    sample_multiplier = 1
+    say(f"Grouping data by queries (target: {min_query_groups} unique queries)...")
+    while len(query_groups) < min_query_groups and sample_multiplier <= 10:
+        sample_size_current = min(sample_size * sample_multiplier, len(dataset))
+        for i in random.sample(range(len(dataset)), sample_size_current):
+            item = dataset[i]
+            group = query_groups.setdefault(item["query_id"], {"query": item["query"], "relevant_docs": {}})
+            group["relevant_docs"].setdefault(item["positive"], None)  # insertion-ordered set
+        sample_multiplier += 1
+    query_ids = sorted(query_groups, key=lambda qid: len(query_groups[qid]["relevant_docs"]), reverse=True)
+    query_ids = query_ids[:min_query_groups]
+    if not query_ids:
+        raise ZeroDivisionError("evaluate_model: no queries to evaluate")
+    rel_docs = [list(query_groups[q]["relevant_docs"]) for q in query_ids]
+    cand_docs = None
+    if candidate_pool_size != -1:
+        cand_docs = []
+        for qi, q in enumerate(query_ids):
+            rel = query_groups[q]["relevant_docs"]
+            # irrelevant = every other selected query's relevant docs (training.py:255-261); sorted so a
+            # seeded run is reproducible (the reference's order depends on PYTHONHASHSEED)
+            irrelevant = sorted({d for o in query_ids if o != q for d in query_groups[o]["relevant_docs"] if d not in rel})
+            if len(irrelevant) > candidate_pool_size:
+                irrelevant = random.sample(irrelevant, candidate_pool_size)
+            cand_docs.append(rel_docs[qi] + irrelevant)
+            if len(cand_docs[-1]) <= 1:
+                raise ValueError("Computing NDCG is only meaningful when there is more than 1 document.")
+    return {"queries": [query_groups[q]["query"] for q in query_ids], "rel_docs": rel_docs, "cand_docs": cand_docs}
+
+
+def _gather_rows(t: torch.Tensor, world: int) -> torch.Tensor:
+    """Concatenates per-rank row blocks of different heights ([n_r, ...] -> [sum n_r, ...], rank order) on every
+    rank: one all-gather of the heights, one of the blocks padded to the tallest."""
+    import torch.distributed as dist
+
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    top = max(ns)
+    pad = torch.zeros((top,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p_[:k] for p_, k in zip(parts, ns)], dim=0)
+
+
 def evaluate_model(
     model: TwoTowersModel,
     dataset,
@@ -541,69 +662,68 @@ def evaluate_model(
 ) -> Union[float, dict[str, float]]:
     """NDCG evaluation with all relevant documents per query (training.py:136-380): same sampling, same
     candidate pools, same metrics and return type; scoring is one batched device pass instead of a per-query
-    CPU cosine + sklearn call."""
-    print(f"Sampling documents for evaluation (initial sample size: {sample_size})...")
+    CPU cosine + sklearn call.
+
+    Under torch.distributed (one process per GPU) the document universe is sharded over the ranks
+    (retrieval.shard_bounds): each rank encodes ITS documents with `encode_documents_batched` — no collective —
+    scans its own shard, and the per-shard top lists meet in one all-gather + tt_topk_merge; the
+    small validation pools gather the shard embeddings instead.  Every rank returns the same value; rank 0 prints."""
+    world, rank = _dist_info()
+    say = print if rank == 0 else (lambda *a, **k: None)
+    say(f"Sampling documents for evaluation (initial sample size: {sample_size})...")
     model.eval()
     clear_gpu_memory()
 
-    # group by query_id until enough unique queries (training.py:184-201; same `random` call sequence)
-    query_groups: dict[int, dict] = {}
-    sample_multiplier = 1
-    print(f"Grouping data by queries (target: {min_query_groups} unique queries)...")
-    while len(query_groups) < min_query_groups and sample_multiplier <= 10:
-        sample_size_current = min(sample_size * sample_multiplier, len(dataset))
-        for i in random.sample(range(len(dataset)), sample_size_current):
-            item = dataset[i]
-            group = query_groups.setdefault(item["query_id"], {"query": item["query"], "relevant_docs": {}})
-            group["relevant_docs"].setdefault(item["positive"], None)  # insertion-ordered set
-        sample_multiplier += 1
-    query_ids = sorted(query_groups, key=lambda qid: len(query_groups[qid]["relevant_docs"]), reverse=True)
-    query_ids = query_ids[:min_query_groups]
-    if not query_ids:
-        raise ZeroDivisionError("evaluate_model: no queries to evaluate")
-    total_relevant_docs = sum(len(query_groups[q]["relevant_docs"]) for q in query_ids)
-    avg_relevant_per_query = total_relevant_docs / len(query_ids)
-    print(f"Selected {len(query_ids)} queries for evaluation")
-    print(f"  Total relevant documents across these queries: {total_relevant_docs}")
-    print(f"  Average relevant docs per query: {avg_relevant_per_query:.2f}")
+    if world > 1:  # one plan for everybody (the sampling uses the process-local `random` state)
+        import torch.distributed as dist
+
+        box = [_eval_plan(dataset, sample_size, min_query_groups, candidate_pool_size, say) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        plan = box[0]
+    else:
+        plan = _eval_plan(dataset, sample_size, min_query_groups, candidate_pool_size, say)
+    queries, rel_docs, cand_docs = plan["queries"], plan["rel_docs"], plan["cand_docs"]
+    n_q = len(queries)
+    total_relevant_docs = sum(len(r) for r in rel_docs)
+    avg_relevant_per_query = total_relevant_docs / n_q
+    say(f"Selected {n_q} queries for evaluation")
+    say(f"  Total relevant documents across these queries: {total_relevant_docs}")
+    say(f"  Average relevant docs per query: {avg_relevant_per_query:.2f}")
 
     # document universe and per-query candidate lists
     full_pool = candidate_pool_size == -1
     if full_pool:
-        print("🚀 Pre-encoding *all* documents for efficiency (this may take a moment)...")
+        say("🚀 Pre-encoding *all* documents for efficiency (this may take a moment)...")
         universe = list(dataset.get_unique_passages())
+        if world > 1:
+            universe = sorted(universe)  # a set-ordered list differs between processes: ids must mean the same everywhere
     else:
-        universe = list(dict.fromkeys(d for q in query_ids for d in query_groups[q]["relevant_docs"]))
+        universe = list(dict.fromkeys(d for r in rel_docs for d in r))
     doc_index = {d: i for i, d in enumerate(universe)}
     if len(universe) <= 1:
         raise ValueError("Computing NDCG is only meaningful when there is more than 1 document.")
-    cand_lists = None
-    if not full_pool:
-        cand_lists = []
-        for q in query_ids:
-            rel = query_groups[q]["relevant_docs"]
-            # irrelevant = every other selected query's relevant docs (training.py:255-261); sorted so a
-            # seeded run is reproducible (the reference's order depends on PYTHONHASHSEED)
-            irrelevant = sorted({d for o in query_ids if o != q for d in query_groups[o]["relevant_docs"] if d not in rel})
-            if len(irrelevant) > candidate_pool_size:
-                irrelevant = random.sample(irrelevant, candidate_pool_size)
-            cand_lists.append([doc_index[d] for d in rel] + [doc_index[d] for d in irrelevant])
-            if len(cand_lists[-1]) <= 1:
-                raise ValueError("Computing NDCG is only meaningful when there is more than 1 document.")
+    cand_lists = None if full_pool else [[doc_index[d] for d in c] for c in cand_docs]
+    lo, hi = retrieval.shard_bounds(len(universe), world, rank)
 
     with torch.no_grad():
-        doc_embeds = model.encode_documents_batched(universe, batch_size=batch_size)
-        query_embeds = model.encode_queries([query_groups[q]["query"] for q in query_ids])
+        query_embeds = model.encode_queries(queries)
+        dev = query_embeds.device
+        if hi > lo:
+            doc_embeds = model.encode_documents_batched(universe[lo:hi], batch_size=batch_size)  # this rank's shard
+        else:
+            doc_embeds = torch.zeros(0, query_embeds.shape[1], dtype=torch.float32, device=dev)
         if full_pool:
-            print(f"🔥 Pre-encoded {len(universe)} documents to reuse for all queries")
-        dev = doc_embeds.device
+            say(f"🔥 Pre-encoded {len(universe)} documents to reuse for all queries")
         Dn = ops.l2_normalize_rows(doc_embeds)  # per-vector clamp of torch.cosine_similarity (training.py:297)
         Qn = ops.l2_normalize_rows(query_embeds)
         if full_pool:
             kk = min(_K_SCAN, len(universe))
-            top_s, top_i = ops.scan_topk(Qn, Dn, k=kk, precision="fp32")
-            pool_sizes = [len(universe)] * len(query_ids)
+            top_s, top_i = ops.scan_topk(Qn, Dn, k=kk, id_base=lo, precision="fp32")
+            top_s, top_i = retrieval.gather_and_merge(top_s, top_i, world)
+            pool_sizes = [len(universe)] * n_q
         else:
+            if world > 1:  # small pools: every rank scores all queries against the gathered shard embeddings
+                Dn = _gather_rows(Dn, world)
             C = max(len(c) for c in cand_lists)
             cand = torch.full((len(cand_lists), C), -1, dtype=torch.int64)
             for r, c in enumerate(cand_lists):
@@ -613,23 +733,30 @@ def evaluate_model(
             top_s, top_i = ops.score_candidates(Qn, Dn, cand, k=kk)
             pool_sizes = [len(c) for c in cand_lists]
         # NDCG on the device (tie-free closed form) ...
-        rel_lists = [sorted(doc_index[d] for d in query_groups[q]["relevant_docs"] if d in doc_index) for q in query_ids]
+        rel_lists = [sorted(doc_index[d] for d in r if d in doc_index) for r in rel_docs]
         offs = torch.tensor(np.concatenate([[0], np.cumsum([len(r) for r in rel_lists])]), dtype=torch.int64, device=dev)
         rel_flat = torch.tensor([d for r in rel_lists for d in r], dtype=torch.int64, device=dev)
         ks = (10, 5, 1) if comprehensive else (10,)
         dev_ndcg = {k: ops.ndcg_at_k(top_i, offs, rel_flat, kk=min(k, kk)).cpu().numpy() for k in ks}
         top_s_h, top_i_h = top_s.cpu().numpy(), top_i.cpu().numpy()
 
-    # ... and exact tie handling for the (rare) queries whose best scores tie past the scanned list
+    # ... and exact tie handling for the (rare) queries whose best scores tie past the scanned list.  The merged lists
+    # are identical on every rank, so all ranks take this path for the same queries (it is collective when sharded).
     def exact(qi: int, k: int) -> float:
-        idx = np.arange(len(universe)) if full_pool else np.array(cand_lists[qi])
-        sc = ops.candidate_scores(Qn[qi: qi + 1], Dn, idx)
+        if full_pool:
+            sc = ops.candidate_scores(Qn[qi: qi + 1], Dn, np.arange(hi - lo)) if hi > lo else np.zeros(0, np.float32)
+            if world > 1:
+                sc = _gather_rows(torch.from_numpy(sc).to(dev), world).cpu().numpy()
+            idx = np.arange(len(universe))
+        else:
+            idx = np.array(cand_lists[qi])
+            sc = ops.candidate_scores(Qn[qi: qi + 1], Dn, idx)
         rel_set_q = set(rel_lists[qi])
         rel = np.array([1 if int(d) in rel_set_q else 0 for d in idx])
         return _tie_averaged_ndcg(rel, sc, k)
 
     scores = {k: [] for k in ks}
-    for qi in range(len(query_ids)):
+    for qi in range(n_q):
         m = int((top_i_h[qi] >= 0).sum())
         has_tie = bool((np.diff(top_s_h[qi][:m]) == 0).any()) if m > 1 else False
         rel_set = set(rel_lists[qi])
@@ -641,46 +768,46 @@ def evaluate_model(
                 scores[k].append(_ndcg_from_lists(top_s_h[qi], top_i_h[qi], rel_set, n_rel, k,
                                                   lambda qi=qi, k=k: exact(qi, k)))
         if qi == 0:
-            print("\nSample evaluation results:")
-            print(f"Query: {query_groups[query_ids[0]]['query']}")
-            print(f"Number of relevant docs: {len(rel_set)}")
-            print(f"Number of candidate docs: {pool_sizes[0]}")
-            print(f"NDCG@10 score for this query: {scores[10][0]:.4f}")
-            print("Top 10 ranked documents:")
-            for rank, d in enumerate(top_i_h[0][:10]):
+            say("\nSample evaluation results:")
+            say(f"Query: {queries[0]}")
+            say(f"Number of relevant docs: {len(rel_set)}")
+            say(f"Number of candidate docs: {pool_sizes[0]}")
+            say(f"NDCG@10 score for this query: {scores[10][0]:.4f}")
+            say("Top 10 ranked documents:")
+            for rank_, d in enumerate(top_i_h[0][:10]):
                 if d < 0:
                     break
                 tag = "RELEVANT" if int(d) in rel_set else "irrelevant"
                 text = str(universe[int(d)])
-                print(f"  {rank + 1}. [{tag}] {text[:100] + '...' if len(text) > 100 else text}")
+                say(f"  {rank_ + 1}. [{tag}] {text[:100] + '...' if len(text) > 100 else text}")
 
     mean_ndcg_10 = float(np.mean(scores[10]))
     if not comprehensive:
-        print(f"\nMean NDCG@10 across {len(query_ids)} queries: {mean_ndcg_10:.4f}")
+        say(f"\nMean NDCG@10 across {n_q} queries: {mean_ndcg_10:.4f}")
         return mean_ndcg_10
     results = {
         f"{wandb_prefix}ndcg_10": mean_ndcg_10,
         f"{wandb_prefix}ndcg_5": float(np.mean(scores[5])),
         f"{wandb_prefix}ndcg_1": float(np.mean(scores[1])),
         f"{wandb_prefix}ndcg_10_std": float(np.std(scores[10])),
-        f"{wandb_prefix}queries_evaluated": len(query_ids),
+        f"{wandb_prefix}queries_evaluated": n_q,
         f"{wandb_prefix}total_relevant_docs": total_relevant_docs,
         f"{wandb_prefix}avg_relevant_per_query": avg_relevant_per_query,
     }
-    print("\n" + "=" * 60)
-    print("COMPREHENSIVE EVALUATION RESULTS")
-    print("=" * 60)
-    print("📊 Performance Metrics:")
-    print(f"   NDCG@1:  {results[f'{wandb_prefix}ndcg_1']:.4f}")
-    print(f"   NDCG@5:  {results[f'{wandb_prefix}ndcg_5']:.4f}")
-    print(f"   NDCG@10: {results[f'{wandb_prefix}ndcg_10']:.4f} (±{results[f'{wandb_prefix}ndcg_10_std']:.4f})")
-    print("\n📈 Evaluation Set Coverage:")
-    print(f"   Queries evaluated: {results[f'{wandb_prefix}queries_evaluated']}")
-    print(f"   Total relevant documents: {results[f'{wandb_prefix}total_relevant_docs']}")
-    print(f"   Avg relevant docs/query: {results[f'{wandb_prefix}avg_relevant_per_query']:.2f}")
-    if log_wandb and wandb is not None:
+    say("\n" + "=" * 60)
+    say("COMPREHENSIVE EVALUATION RESULTS")
+    say("=" * 60)
+    say("📊 Performance Metrics:")
+    say(f"   NDCG@1:  {results[f'{wandb_prefix}ndcg_1']:.4f}")
+    say(f"   NDCG@5:  {results[f'{wandb_prefix}ndcg_5']:.4f}")
+    say(f"   NDCG@10: {results[f'{wandb_prefix}ndcg_10']:.4f} (±{results[f'{wandb_prefix}ndcg_10_std']:.4f})")
+    say("\n📈 Evaluation Set Coverage:")
+    say(f"   Queries evaluated: {results[f'{wandb_prefix}queries_evaluated']}")
+    say(f"   Total relevant documents: {results[f'{wandb_prefix}total_relevant_docs']}")
+    say(f"   Avg relevant docs/query: {results[f'{wandb_prefix}avg_relevant_per_query']:.2f}")
+    if log_wandb and wandb is not None and rank == 0:
         wandb.log(results)
-        print("\n✅ Comprehensive test results logged to wandb")
+        say("\n✅ Comprehensive test results logged to wandb")
     return results
 
 
@@ -707,22 +834,40 @@ def run_training(
     """Main training function (training.py:383-529).  `fused` (additive) selects the FusedTrainer; by
     default it is used whenever the dataset is token-bank backed and no gradient accumulation / wandb
     gradient hooks require the reference-shaped loop."""
-    print("Initializing model and data...")
+    # one process per GPU under torchrun / torch.distributed.run (SURVEY.md §8e): `batch_size` is the GLOBAL batch,
+    # every rank trains on its contiguous slice and evaluates its shard of the documents
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    say = print if rank == 0 else (lambda *a, **k: None)
+    say("Initializing model and data...")
     if not torch.cuda.is_available():
         raise RuntimeError("two-towers-overlords_b200 needs a CUDA (sm_100a) device; there is no CPU path")
-    device = torch.device("cuda")
-    print(f"Using device: {device}")
-    print(f"GPU: {torch.cuda.get_device_name(0)}")
-    print(f"Memory: {torch.cuda.get_device_properties(0).total_memory / 1e9:.1f}GB")
+    if world > 1:
+        import torch.distributed as dist
 
-    use_wandb = bool(use_wandb and wandb is not None)
+        torch.cuda.set_device(local_rank)
+        device = torch.device("cuda", local_rank)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+        if batch_size % world != 0:
+            raise ValueError(f"batch_size {batch_size} (the global batch) must be a multiple of WORLD_SIZE {world}")
+    else:
+        device = torch.device("cuda")
+    say(f"Using device: {device}")
+    say(f"GPU: {torch.cuda.get_device_name(device)}")
+    say(f"Memory: {torch.cuda.get_device_properties(device).total_memory / 1e9:.1f}GB")
+    if world > 1:
+        say(f"Data parallel over {world} GPUs: global batch {batch_size}, {batch_size // world} triplets per GPU")
+
+    use_wandb = bool(use_wandb and wandb is not None and rank == 0)
     if use_wandb:
         config = {
             "epochs": num_epochs, "batch_size": batch_size, "learning_rate": learning_rate,
             "max_samples": max_samples, "model_name": "sentence-transformers/all-MiniLM-L6-v2",
             "loss_function": "triplet_loss", "distance_metric": "cosine", "margin": margin,
             "dataset_type": "ms_marco_all_passages", "device": str(device),
-            "device_name": torch.cuda.get_device_name(0),
+            "device_name": torch.cuda.get_device_name(device),
         }
         if wandb_config:
             config.update(wandb_config)
@@ -730,10 +875,14 @@ def run_training(
             wandb.init(project=project_name, config=config)
 
     model = TwoTowersModel(projection_dim=projection_dim, table_dtype=table_dtype).to(device)
+    if world > 1:  # random-init tables and projections are drawn per process: rank 0's become everybody's
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
     criterion = TripletLoss(margin=margin)
     optimizer = torch.optim.Adam(model.parameters(), lr=learning_rate)
     if use_wandb:
-        wandb.watch(model, log="all", log_freq=100)
+        if world == 1:
+            wandb.watch(model, log="all", log_freq=100)
         wandb.log({"total_parameters": sum(p.numel() for p in model.parameters())})
 
     train_ds = MSMarcoDataset("train", max_samples=max_samples)
@@ -743,36 +892,50 @@ def run_training(
         tok = ds.tokenizer() if hasattr(ds, "tokenizer") else None
         if tok is not None:
             for d in more:
-                tok.banks.update(d.tokenizer().banks)
+                tok.add(d.tokenizer())
             model.query_tower.tokenizer = model.document_tower.tokenizer = tok
         return tok
 
     bank_backed = use_bank_tokenizer(train_ds, val_ds) is not None
     train_dl = TripletDataLoader(train_ds, batch_size=batch_size, num_workers=num_workers, device=device)
     if fused is None:
-        fused = bank_backed and accumulation_steps == 1 and not use_wandb
+        # one GPU: the reference-shaped loops serve gradient accumulation and wandb's gradient hooks; several GPUs:
+        # only the fused step exchanges gradients, so it is the path (accumulation folds into the larger global batch)
+        fused = bank_backed and (world > 1 or (accumulation_steps == 1 and not use_wandb))
+    if world > 1 and not fused:
+        raise ValueError("data-parallel training needs the fused step (a token-bank dataset and fused != False)")
+    if world > 1 and accumulation_steps != 1:
+        say(f"  note: accumulation_steps={accumulation_steps} is ignored under data parallelism; the global batch "
+            f"of {batch_size} triplets is one optimiser step")
 
-    print("Training configuration:")
-    print(f"  Physical batch size: {batch_size}")
-    print(f"  Gradient accumulation steps: {accumulation_steps}")
-    print(f"  Effective batch size: {batch_size * accumulation_steps}")
-    print(f"  Mixed precision: {use_mixed_precision}")
-    print(f"  DataLoader workers: {num_workers}")
-    print(f"  Fused B200 step: {fused}")
+    say("Training configuration:")
+    say(f"  Physical batch size: {batch_size}")
+    say(f"  Gradient accumulation steps: {accumulation_steps}")
+    say(f"  Effective batch size: {batch_size * (accumulation_steps if world == 1 else 1)}")
+    say(f"  Mixed precision: {use_mixed_precision}")
+    say(f"  DataLoader workers: {num_workers}")
+    say(f"  Fused B200 step: {fused}")
 
     scaler = GradScaler(device.type) if use_mixed_precision else None
     trainer = token_dl = feeder = None
     if fused:
-        trainer = FusedTrainer(model, margin, learning_rate, batch_size, token_slots=2)
+        seed_box = [random.randrange(2 ** 31)]
+        if world > 1:  # the epoch permutation and the in-batch negatives are functions of this seed: share rank 0's
+            dist.broadcast_object_list(seed_box, src=0)
+        trainer = FusedTrainer(model, margin, learning_rate, batch_size // world, token_slots=2, world_size=world,
+                               rank=rank)
         if os.environ.get("TT_HOST_FEEDER") == "1" or len(train_ds) < 2 * batch_size:
-            token_dl = TokenTripletLoader(train_ds, batch_size, trainer.Lq, trainer.Ld)  # host-assembled batches
+            # host-assembled batches (negatives drawn over the global batch, this rank's slice)
+            token_dl = TokenTripletLoader(train_ds, batch_size, trainer.Lq, trainer.Ld, rank=rank, world_size=world,
+                                          seed=seed_box[0])
         else:  # token bank resident in HBM, batches (and in-batch negatives) assembled by one kernel per step
-            feeder = DeviceTripletFeeder(train_ds, batch_size, trainer.Lq, trainer.Ld, device,
-                                         seed=random.randrange(2 ** 31))
+            feeder = DeviceTripletFeeder(train_ds, batch_size, trainer.Lq, trainer.Ld, device, rank=rank,
+                                         world_size=world, seed=seed_box[0])
+        trainer.prepare(2)
 
-    print(f"Starting training for {num_epochs} epochs...")
+    say(f"Starting training for {num_epochs} epochs...")
     for epoch in range(num_epochs):
-        print(f"\nEpoch {epoch + 1}/{num_epochs}")
+        say(f"\nEpoch {epoch + 1}/{num_epochs}")
         if trainer is not None and feeder is not None:
             avg_loss = trainer.train_epoch_device(feeder, log_every=10)
         elif trainer is not None:
@@ -783,23 +946,28 @@ def run_training(
                                              accumulation_steps=accumulation_steps, log_wandb=use_wandb)
         else:
             avg_loss = train_epoch(model, train_dl, criterion, optimizer, log_wandb=use_wandb)
-        print(f"Average training loss: {avg_loss:.4f}")
+        say(f"Average training loss: {avg_loss:.4f}")
         ndcg = evaluate_model(model, val_ds, batch_size=batch_size)
-        print(f"Validation NDCG@10: {ndcg:.4f}")
+        say(f"Validation NDCG@10: {ndcg:.4f}")
+        if trainer is not None:
+            trainer.sync_ranks()  # evaluation time differs per rank: line up before the next exchanged step
         if use_wandb:
             wandb.log({"epoch": epoch + 1, "avg_train_loss": avg_loss, "val_ndcg_10": ndcg})
 
-    print("\n" + "=" * 60)
+    say("\n" + "=" * 60)
     if run_comprehensive_test:
-        print("TRAINING COMPLETED - Starting comprehensive testing")
-        print("=" * 60)
+        say("TRAINING COMPLETED - Starting comprehensive testing")
+        say("=" * 60)
         test_dataset = MSMarcoDataset("test", max_samples=10_000)
         use_bank_tokenizer(train_ds, val_ds, test_dataset)
         _ = evaluate_model(model=model, dataset=test_dataset, min_query_groups=200, candidate_pool_size=-1,
                            comprehensive=True, log_wandb=use_wandb, batch_size=batch_size)
     else:
-        print("TRAINING COMPLETED - Skipping comprehensive testing")
-        print("=" * 60)
+        say("TRAINING COMPLETED - Skipping comprehensive testing")
+        say("=" * 60)
+    if trainer is not None and world > 1:
+        trainer.sync_ranks()
+        trainer.close()  # parameters move out of the peer segment so the returned model outlives it
     if use_wandb:
         wandb.finish()
     return model
