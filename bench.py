@@ -154,6 +154,36 @@ def cpu_train_throughput(budget_s: float, steps: int | None = None, warmup: int 
                             "ms_per_step": 1e3 * dt / steps}
 
 
+def cpu_eval_throughput(n_docs_full: int, P: int, budget_s: float = 12.0, n_sample_docs: int = 1_000_000):
+    """The reference's eval inner loop (backend/training.py:297-304: per query a CPU cosine_similarity against all
+    documents + sklearn-semantics ndcg_score, restated in oracle.retrieval_eval) on a 1 M-document sample with the
+    host cores, extrapolated linearly in the document count to the full corpus."""
+    from oracle import two_towers_oracle as O
+
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        pass
+    g = torch.Generator().manual_seed(7)
+    n = min(n_sample_docs, n_docs_full)
+    De = torch.randn(n, P, generator=g)
+    Qe = torch.randn(16, P, generator=g)
+    rel = [set(range(i, i + 5)) for i in range(16)]
+    t0 = time.perf_counter()
+    O.retrieval_eval(Qe[:1], De, rel[:1], k=10)
+    t_first = time.perf_counter() - t0
+    nq = int(max(2, min(15, budget_s / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    O.retrieval_eval(Qe[1: 1 + nq], De, rel[1: 1 + nq], k=10)
+    dt = time.perf_counter() - t0
+    qps_sample = nq / dt
+    return {"value": qps_sample * n / n_docs_full, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "measured_queries_per_s_on_sample": qps_sample, "seconds_per_query_on_sample": dt / nq,
+            "sample": f"{nq} queries x {n} documents x {P}-d in {dt:.1f} s (oracle.retrieval_eval = the reference's "
+                      f"per-query cosine_similarity + ndcg_score loop, torch/numpy CPU, {torch.get_num_threads()} "
+                      f"threads), extrapolated linearly in the document count to {n_docs_full}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,19 +200,20 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1, "fp32", "f32") | {"cpu_sample_batch": B},
+        "config": workload_config(args.gpus), "variant": {"arithmetic": "fp32 torch CPU", "cpu_sample_batch": B},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def workload_config(world, precision, table_dtype):
+def workload_config(world):
+    """The workload both arms run (identical dict in both JSON lines); how each arm computes it is in `variant`."""
     return {
         "workload": "configs[1] heavy GPU run shape: triplet training step, batch 2048/GPU, proj-dim 512, "
-                    "query 32 / doc 256 tokens (shape U), margin 0.3, Adam lr 1e-3, random-init 30522x384 tables",
+                    "query 32 / doc 256 tokens (shape U), margin 0.3, Adam lr 1e-3, random-init 30522x384 fp32 tables",
         "global_batch": B_PER_GPU * world, "batch_per_gpu": B_PER_GPU, "projection_dim": P_DIM, "Lq": LQ, "Ld": LD,
-        "parallelism": f"dp{world}", "projection_precision": precision, "table_dtype": table_dtype,
+        "parallelism": f"dp{world}",
         "l2": f"inputs rotate over {N_TOKEN_SETS} token batches (>= {N_TOKEN_SETS * 3.34:.0f} MB > 126 MB L2); the two "
               "token tables are weights and stay cache-warm across steps as in real training",
     }
@@ -257,12 +288,14 @@ def run_b200(args):
     if trainer.xchg is not None:
         trainer.xchg.reset_timing()
     t_wall0 = time.time()
+    cap0 = trainer.graph_captures
     ev0.record()
     for i in range(K):
         trainer.step((W + i) % NS, (W + i + 1) % NS)  # the next step's pooled gather runs beside this step
     ev1.record()
     barrier()
     t_wall1 = time.time()
+    captures_in_timed = {"value_leg": trainer.graph_captures - cap0}
     exchange_us = None
     if trainer.xchg is not None:
         t_wait, t_rest, n_calls, t_push = trainer.xchg.timing()
@@ -308,11 +341,15 @@ def run_b200(args):
         e2e_step(i)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cap0 = trainer.graph_captures
     ev0.record()
     for i in range(W, W + K):
         e2e_step(i)
     ev1.record()
     barrier()
+    captures_in_timed["e2e_leg"] = trainer.graph_captures - cap0
+    if not args.no_graph and any(captures_in_timed.values()):
+        raise SystemExit(f"a CUDA graph was captured inside a timed region: {captures_in_timed}")
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
     e2e_value = B_PER_GPU * world * K / (e2e_ms * 1e-3)
 
@@ -363,20 +400,47 @@ def run_b200(args):
     pool_ms = ev0.elapsed_time(ev1) / K
     hbm_peak, tensor_peak, peak_kind = peaks()
     achieved = alg_bytes_per_triplet * B_PER_GPU / (pool_ms * 1e-3) / 1e9
+    # measured L2 -> SM read ceiling (tt_ubench_l2_read): the gather's tables are cache-resident, so THIS is the
+    # bandwidth that bounds it; probed at one table (47 MB) and at both (94 MB), the larger figure is the peak
+    l2 = {}
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    for label, nbytes in (("one_table_47MB", VOCAB * HIDDEN * 4), ("two_tables_94MB", 2 * VOCAB * HIDDEN * 4)):
+        probe = torch.empty(nbytes // 4, dtype=torch.float32, device=dev).normal_()
+        its = 40
+        for _ in range(2):
+            _native.check(lib.tt_ubench_l2_read(probe.data_ptr(), nbytes, its, 8, sink.data_ptr(), _native.stream()), "l2")
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _native.check(lib.tt_ubench_l2_read(probe.data_ptr(), nbytes, its, 8, sink.data_ptr(), _native.stream()), "l2")
+        ev1.record()
+        torch.cuda.synchronize()
+        l2[label] = nbytes * its / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        del probe
+    l2_peak = max(l2.values())
     roofline = {
         "kernel": "pool_fwd_kernel (token-row gather + masked mean + L2 normalise, q|p|n in one launch)",
-        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s",
-        "frac": achieved / hbm_peak,
+        "bound": "l2", "achieved": achieved, "peak": l2_peak, "peak_kind": "measured in this run (tt_ubench_l2_read)",
+        "unit": "GB/s", "frac": achieved / l2_peak, "l2_probe_gbs": l2,
         "traffic": ncu_traffic("pool_fwd_kernel") if table_dtype == torch.float32 else None,
+        "hbm_formula": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s",
+                        "frac": achieved / hbm_peak,
+                        "note": "the contract's formula (algorithmic bytes / time / HBM copy peak): both 46.9 MB fp32 "
+                                "tables fit the 126 MB L2, DRAM traffic is ~7 % of the algorithmic bytes, so this "
+                                "fraction exceeds 1 and is not a roofline; the L2 figure above is"},
         "algorithmic_bytes_per_launch": alg_bytes_per_triplet * B_PER_GPU, "us_per_launch": pool_ms * 1e3,
         "share_of_step": pool_ms / (ms_total / K),
         "share_of_serialised_step": pool_ms / seq_ms, "serialised_step_ms": seq_ms,
         "share_note": "timed alone; inside a step this kernel (for step i+1) runs BESIDE the tensor-core chain of "
                       "step i, so the shares of the two do not add up to 1; share_of_serialised_step divides by the "
                       "step time with nothing overlapped and is the figure to compare with the ncu launch list",
-        "note": "both 46.9 MB fp32 tables fit the 126 MB L2, so DRAM traffic is far below the algorithmic bytes "
-                "and frac can exceed 1 (SURVEY.md §7); see profiles/ for dram__bytes and L2 throughput",
     }
+
+    # ---- data-parallel parity on real peers (N > 1): replicas bit-identical, and equal (to rounding) to ONE rank
+    # running the same global batch ---------------------------------------------------------------------------------
+    dp_check = None
+    if world > 1:
+        dp_check = run_dp_check(dev, world, rank, args, ids_dtype, mask_dtype)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------------
     cpu = None
@@ -389,18 +453,27 @@ def run_b200(args):
     exchange_kind = trainer.exchange
     barrier()
     trainer.close()
+    del trainer, model
+    torch.cuda.empty_cache()
+    config2 = run_config2(dev, world, rank, args) if not args.no_config2 else None
+    epoch_leg = run_epoch_leg(dev, world, rank, args) if not args.no_epoch else None
+    torch.cuda.empty_cache()
     scan = None
     if not args.no_scan:
-        del trainer, model
-        torch.cuda.empty_cache()
         scan = run_scan(dev, world, rank, args.scan_docs, args.scan_queries, HIDDEN, args.scan_passes)
+        if scan is not None and rank == 0 and world == 1 and not args.no_cpu:
+            scan["cpu_baseline"] = cpu_eval_throughput(args.scan_docs, HIDDEN, args.cpu_budget)
 
     if rank == 0:
         emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else f"f32 ({args.precision} tensor-core projection)",
-            "data": "synthetic", "config": workload_config(world, args.precision, args.table_dtype) | {"dp_exchange": exchange_kind, "token_dtypes": f"ids {args.ids_dtype}, mask u8"},
+            "data": "synthetic", "config": workload_config(world),
+            "variant": {"projection_precision": args.precision, "table_dtype": args.table_dtype,
+                        "dp_exchange": exchange_kind, "token_dtypes": f"ids {args.ids_dtype}, mask u8"},
+            "graph_captures_in_timed_region": captures_in_timed, "dp_check": dp_check, "config2": config2,
+            "epoch_leg": epoch_leg,
             "dp_exchange_us": exchange_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
@@ -410,6 +483,216 @@ def run_b200(args):
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# data-parallel parity on real peers
+# --------------------------------------------------------------------------------------------------
+def run_dp_check(dev, world, rank, args, ids_dtype, mask_dtype, n_steps=2):
+    """(a) after `n_steps` exchanged steps every rank holds bit-identical parameters; (b) they equal, to rounding, the
+    parameters ONE rank reaches on the same global batches (rank-ordered concatenation of the per-rank batches,
+    inv_batch = 1 / global batch).  Fresh models from the same seed; eager steps (no graphs)."""
+    import torch.distributed as dist
+
+    from two_towers_overlords_b200 import TwoTowersModel
+    from two_towers_overlords_b200.training import FusedTrainer
+
+    def fresh(batch, w, r):
+        torch.manual_seed(0)
+        m = TwoTowersModel(projection_dim=P_DIM, precision=args.precision).to(dev)
+        return m, FusedTrainer(m, MARGIN, LR, batch, LQ, LD, precision=args.precision, world_size=w, rank=r,
+                               use_graph=False, ids_dtype=ids_dtype, mask_dtype=mask_dtype)
+
+    m_dp, t_dp = fresh(B_PER_GPU, world, rank)
+    p0 = t_dp.flat_p.clone()
+    sets = token_sets(n_steps, B_PER_GPU, 4321 + rank, ids_dtype, mask_dtype, pin=False)
+    losses = []
+    for ts in sets:
+        for dst, src in zip(t_dp.tok, ts):
+            dst.copy_(src)
+        t_dp.step()
+        losses.append(float(t_dp.loss_view[0].item()))
+    torch.cuda.synchronize()
+    t_dp.check()
+    mine = t_dp.flat_p.clone()
+    bits = mine.view(torch.int32).to(torch.int64)
+    digest = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev)).sum()])
+    digests = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(digests, digest)
+    identical = all(torch.equal(d, digests[0]) for d in digests)
+    dist.barrier()
+    t_dp.close()
+    out = {"steps": n_steps, "replicas_bit_identical": bool(identical), "loss_dp": losses}
+    if rank == 0:  # the same global batches on one rank
+        m_1, t_1 = fresh(B_PER_GPU * world, 1, 0)
+        all_sets = [token_sets(n_steps, B_PER_GPU, 4321 + r, ids_dtype, mask_dtype, pin=False) for r in range(world)]
+        l1 = []
+        for s_ in range(n_steps):
+            for j, dst in enumerate(t_1.tok):
+                dst.copy_(torch.cat([all_sets[r][s_][j] for r in range(world)]))
+            t_1.step()
+            l1.append(float(t_1.loss_view[0].item()))
+        torch.cuda.synchronize()
+        upd_dp, upd_1 = (mine - p0).double(), (t_1.flat_p - p0).double()
+        out["loss_one_rank"] = l1
+        out["loss_rel_err_vs_one_rank"] = max(abs(a - b) / abs(b) for a, b in zip(losses, l1))
+        out["update_rel_err_vs_one_rank"] = float((upd_dp - upd_1).norm() / upd_1.norm())
+        out["note"] = ("update = parameters after the steps minus the initial ones (norm-wise; Adam's g/(|g|+eps) amplifies "
+                       "rounding of near-zero gradient elements, and the summation order differs: per-rank sums added in "
+                       "rank order vs one sum over the global batch)")
+        del t_1, m_1
+    dist.barrier()
+    ok = torch.tensor([1 if identical else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        raise SystemExit("dp_check: data-parallel replicas diverged")
+    if rank == 0 and (out["loss_rel_err_vs_one_rank"] > 1e-5 or out["update_rel_err_vs_one_rank"] > 5e-3):
+        raise SystemExit(f"dp_check: data-parallel result differs from the one-rank run: {out}")
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# configs[2]: saved-model shape, trainable token tables (sorted-segment scatter-add backward)
+# --------------------------------------------------------------------------------------------------
+def run_config2(dev, world, rank, args, B=4096, P=384, steps=12):
+    """Per-GPU batch 4096, P = 384, 32/256-token rows, BOTH 30522x384 tables trainable: the whole step (gather -> MLPs
+    -> loss -> projection gradients -> dx -> both scatter-adds) and the document-table scatter-add (tt_pool_bwd) alone
+    with its HBM roofline (SURVEY.md §8d formula).  Every rank runs its own replica (no exchange: the table gradient
+    all-reduce is not part of this leg)."""
+    from two_towers_overlords_b200 import TwoTowersModel, _native
+    from two_towers_overlords_b200.training import FusedTrainer
+
+    lib = _native.load()
+    hbm_peak, _, peak_kind = peaks()
+    torch.manual_seed(1)
+    m = TwoTowersModel(projection_dim=P, precision=args.precision, train_table=True).to(dev)
+    tr = FusedTrainer(m, MARGIN, LR, B, LQ, LD, precision=args.precision, use_graph=False, ids_dtype=torch.int32,
+                      mask_dtype=torch.uint8, token_slots=4)
+    sets = token_sets(4, B, 99 + rank, torch.int32, torch.uint8, pin=False)
+    for slot, ts in enumerate(sets):
+        for dst, src in zip(tr.tok_slots[slot], ts):
+            dst.copy_(src)
+    for i in range(3):
+        tr.step(i % 4)
+    torch.cuda.synchronize()
+    n0 = lib.tt_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        tr.step(i % 4)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    launches = (lib.tt_launch_count() - n0) // steps
+    # the document-table scatter-add alone: rows p | n (2B sequences of 256 tokens), gradient rows g [2B,384]
+    ids = torch.cat([tr.tok_slots[0][2], tr.tok_slots[0][4]]).contiguous()
+    mask = torch.cat([tr.tok_slots[0][3], tr.tok_slots[0][5]]).contiguous()
+    R = ids.shape[0]
+    dx = torch.randn(R, HIDDEN, device=dev)
+    xh = torch.nn.functional.normalize(torch.randn(R, HIDDEN, device=dev), dim=1)
+    cnt = torch.full((R,), float(LD), device=dev)
+    nrm = torch.ones(R, device=dev)
+    dtab = torch.empty(VOCAB, HIDDEN, device=dev)
+    ws_bytes = lib.tt_pool_bwd_ws_bytes(R, LD, VOCAB, HIDDEN)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    def bwd():
+        _native.check(lib.tt_pool_bwd(dx.data_ptr(), xh.data_ptr(), cnt.data_ptr(), nrm.data_ptr(), ids.data_ptr(),
+                                      _native.dtype_code(ids), mask.data_ptr(), _native.dtype_code(mask), R, LD, VOCAB,
+                                      HIDDEN, dtab.data_ptr(), 0, ws.data_ptr(), ws_bytes, _native.stream()),
+                      "tt_pool_bwd")
+
+    for _ in range(3):
+        bwd()
+    torch.cuda.synchronize()
+    n1 = lib.tt_launch_count()
+    ev0.record()
+    for _ in range(steps):
+        bwd()
+    ev1.record()
+    torch.cuda.synchronize()
+    bwd_ms = ev0.elapsed_time(ev1) / steps
+    bwd_launches = (lib.tt_launch_count() - n1) // steps
+    n_unique = int(torch.unique(ids[mask.bool()].to(torch.int64)).numel())
+    alg = R * LD * (4 + 1) + R * LD * 8 + R * HIDDEN * 4 + n_unique * HIDDEN * 4 + (VOCAB - n_unique) * HIDDEN * 4
+    out = {
+        "workload": "configs[2] saved-model shape e15.lr4.d384.m3: batch 4096/GPU, proj-dim 384, query 32 / doc 256 "
+                    "tokens, both 30522x384 tables trainable (deterministic sorted-segment scatter-add backward)",
+        "metric": METRIC, "value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        "gpu_launches_per_step": int(launches), "n_gpus": world, "scaling": "replicas (no exchange in this leg)",
+        "roofline_pool_bwd": {
+            "kernel": "tt_pool_bwd (document table: 2B x 256 tokens -> radix sort by id -> one warp per touched row)",
+            "bound": "hbm", "achieved": alg / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "peak_kind": peak_kind,
+            "unit": "GB/s", "frac": alg / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_call": bwd_ms,
+            "launches_per_call": int(bwd_launches), "algorithmic_bytes_per_call": alg, "unique_rows": n_unique,
+            "traffic": None,
+            "formula": "tokens*(4 B id + 1 B mask) + tokens*8 B sort keys (id, position) + rows*1536 B gradient rows "
+                       "read + 30522*1536 B table gradient written (touched rows summed, the rest zero-filled)"},
+    }
+    del tr, m
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# configs[3]: one full-dataset-sized pass through the public epoch loop + NDCG@10
+# --------------------------------------------------------------------------------------------------
+def run_epoch_leg(dev, world, rank, args):
+    """~800k synthetic MS MARCO-shaped triplets, global batch 2048 x N (16384 on 8 GPUs), batches assembled on the
+    device (DeviceTripletFeeder), FusedTrainer.train_epoch_device, then evaluate_model (NDCG@10, sharded over the
+    ranks) — the calls run_training makes for one epoch, timed on the device, max over ranks."""
+    import contextlib
+    import io
+
+    import torch.distributed as dist
+
+    from two_towers_overlords_b200 import TwoTowersModel
+    from two_towers_overlords_b200.data import DeviceTripletFeeder, MSMarcoDataset
+    from two_towers_overlords_b200.training import FusedTrainer, evaluate_model
+
+    gb = B_PER_GPU * world
+    with contextlib.redirect_stdout(io.StringIO()):
+        train_ds = MSMarcoDataset("train", max_samples=args.epoch_triplets, synthetic=True)
+        val_ds = MSMarcoDataset("validation", max_samples=1000, synthetic=True)
+    torch.manual_seed(0)
+    m = TwoTowersModel(projection_dim=P_DIM, precision=args.precision).to(dev)
+    tok = train_ds.tokenizer()
+    tok.add(val_ds.tokenizer())
+    m.query_tower.tokenizer = m.document_tower.tokenizer = tok
+    tr = FusedTrainer(m, MARGIN, LR, B_PER_GPU, LQ, LD, precision=args.precision, world_size=world, rank=rank,
+                      token_slots=2)
+    feeder = DeviceTripletFeeder(train_ds, gb, LQ, LD, dev, rank=rank, world_size=world, seed=17)
+    tr.prepare(2)
+    steps = len(feeder)
+    for _ in range(1):  # untimed pass: first-use graphs of the epoch tail, allocator warm-up
+        tr.train_epoch_device(feeder)
+    tr.sync_ranks()
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ev0.record()
+    avg = tr.train_epoch_device(feeder)
+    ev1.record()
+    import random as _random
+    _random.seed(5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ndcg = evaluate_model(m, val_ds, batch_size=gb)
+    ev2.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    train_ms, eval_ms = float(t[0]), float(t[1])
+    tr.sync_ranks()
+    tr.close()
+    out = {"workload": "configs[3] full-dataset pass: synthetic MS MARCO-shaped pairs, global batch 2048 x N, "
+                       "device-assembled batches, NDCG@10 evaluation at the end of the epoch",
+           "triplets": steps * gb, "global_batch": gb, "steps": steps, "epoch_ms": train_ms,
+           "triplets_per_s": steps * gb / (train_ms * 1e-3), "avg_loss": avg, "eval_ms": eval_ms, "val_ndcg_10": ndcg,
+           "note": "includes per-step batch assembly on the device and the host-side launch loop; evaluate_model = "
+                   "sampling + sharded document encode + candidate scoring + NDCG@10 (20 queries, reference defaults)"}
+    del tr, m, feeder
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -560,6 +843,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-scan", action="store_true")
+    ap.add_argument("--no-config2", action="store_true", help="skip the configs[2] leg (trainable tables, B=4096, P=384)")
+    ap.add_argument("--no-epoch", action="store_true", help="skip the configs[3] leg (~800k-triplet pass + NDCG@10)")
+    ap.add_argument("--epoch-triplets", type=int, default=800_000)
     ap.add_argument("--scan-docs", type=int, default=8_800_000)
     ap.add_argument("--scan-queries", type=int, default=100_000)
     ap.add_argument("--scan-passes", type=int, default=2)

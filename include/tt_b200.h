@@ -289,6 +289,14 @@ int tt_assemble_triplets(const tt_token_bank* qbank, const tt_token_bank* dbank,
                          void* n_ids, void* n_mask, int ids_dtype, int mask_dtype, int32_t* neg_out, int* err_flag,
                          tt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement probe (bench.py): L2 -> SM read bandwidth.  Every SM streams `buf` (`bytes` long, cache-resident
+ * when it fits the 126 MB L2) `iters` times with coalesced 16-byte loads at full occupancy; the caller times the
+ * launch with CUDA events: GB/s = bytes * iters / seconds.  This is the ceiling of the pooled gather, whose token
+ * tables stay resident in L2 (the reference's counterpart is nn.Embedding inside backend/model.py:51-52).
+ * ctas_per_sm <= 0 selects 8 (x 256 threads).  sink: 4 writable bytes. */
+int tt_ubench_l2_read(const void* buf, size_t bytes, int iters, int ctas_per_sm, void* sink, tt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

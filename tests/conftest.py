@@ -30,10 +30,13 @@ def pytest_sessionstart(session):
     spec.loader.exec_module(mod)
     try:
         mod.build()
-    except Exception as e:  # noqa: BLE001  (an existing library still gets tested; a missing one fails loudly later)
-        if not os.path.exists(mod.LIB):
-            raise
-        print(f"warning: could not refresh {mod.LIB}: {e}")
+    except Exception as e:  # noqa: BLE001
+        # a library that is missing or OLDER than any source must never be tested silently
+        srcs = [os.path.join(mod.HERE, f) for f in os.listdir(mod.HERE) if f.endswith((".cu", ".cuh"))]
+        srcs.append(os.path.join(ROOT, "include", "tt_b200.h"))
+        if not os.path.exists(mod.LIB) or any(os.path.getmtime(f) > os.path.getmtime(mod.LIB) for f in srcs):
+            raise RuntimeError(f"{mod.LIB} is missing or older than its sources and could not be rebuilt: {e}") from e
+        print(f"warning: could not re-run the build, but {mod.LIB} is newer than every source: {e}")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -341,5 +341,5 @@ def test_bench_synthetic_token_sets_follow_the_stated_shape():
         assert not any(torch.equal(pi[i], ni[i]) for i in range(64))          # never its own positive
         assert all(any(torch.equal(ni[i], pi[j]) for j in range(64)) for i in range(0, 64, 9))  # an in-batch positive
         assert all(torch.equal(x, y) for x, y in zip(sa, sb))
-    cfg = bench.workload_config(8, "bf16x3", "f32")
+    cfg = bench.workload_config(8)
     assert cfg["global_batch"] == 8 * bench.B_PER_GPU and cfg["parallelism"] == "dp8" and "workload" in cfg

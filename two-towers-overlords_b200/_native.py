@@ -109,6 +109,7 @@ _SIGNATURES = {
     "tt_assemble_triplets": (c_int, [POINTER(TokenBankDesc), POINTER(TokenBankDesc), c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, ctypes.c_uint64, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tt_ubench_l2_read": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "tt_peer_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
     "tt_peer_topk_merge": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),
