@@ -49,14 +49,58 @@ def oracle_twin(m, P, vocab, train_table=False):
     return ref
 
 
-def oracle_grads(ref, batch, margin):
-    q = ref.encode_queries(batch.q_ids, batch.q_mask)
-    p = ref.encode_documents(batch.p_ids, batch.p_mask)
-    n = ref.encode_documents(batch.n_ids, batch.n_mask)
-    loss = O.triplet_loss(q, p, n, margin)
+KINK_BAND = 2e-6  # |pre-activation| below which the ReLU gate is undecided between two fp32 summation orders
+
+
+def oracle_grads(ref, batch, margin, gate=None):
+    """Loss and the 8 projection gradients of the oracle (+ table gradients when they train).  Also returns the
+    first-layer pre-activations z [3B,P] (rows q | p | n).
+
+    `gate` (bool [3B,P], optional): the ReLU gate to differentiate through instead of the oracle's own `z > 0`.
+    ReLU is not differentiable at 0: an element whose pre-activation lies within rounding error of zero (|z| of a few
+    1e-8 against a scale of 3e-2) gets gate 1 from one correct fp32 summation order and gate 0 from another — the
+    CPU oracle itself flips ~0.4 such elements per configs[1] step against float64.  ONE flipped element moves a
+    weight gradient by ~1e-3 of its norm (its rank-1 term is as large as any other of the 3.1 M, and the gradient is
+    a sum of random signs), so the 1e-3 gradient gate is only meaningful with the same gate on both sides — exactly
+    like the top-10 id rule, which is exact "wherever score gaps exceed 1e-5".  The tests therefore (1) require every
+    gate disagreement to sit inside |z| <= KINK_BAND, (2) count them, and (3) compare gradients with the oracle
+    differentiated through the device's gate; the forward value is unchanged by more than KINK_BAND."""
+    for prm in ref.parameters():
+        prm.grad = None
+    ys, zs = [], []
+    B = batch.q_ids.shape[0]
+    for g, (tower, ids, mask) in enumerate(((ref.query_tower, batch.q_ids, batch.q_mask),
+                                            (ref.document_tower, batch.p_ids, batch.p_mask),
+                                            (ref.document_tower, batch.n_ids, batch.n_mask))):
+        if tower.table.requires_grad:
+            emb = torch.nn.functional.embedding(ids.long(), tower.table)
+        else:
+            with torch.no_grad():
+                emb = torch.nn.functional.embedding(ids.long(), tower.table)
+        x = torch.nn.functional.normalize(O.mean_pooling(emb, mask.long()), p=2, dim=1)
+        z = torch.nn.functional.linear(x, tower.projection[0].weight, tower.projection[0].bias)
+        h = torch.relu(z) if gate is None else z * gate[g * B: (g + 1) * B].to(z.dtype)
+        ys.append(torch.nn.functional.linear(h, tower.projection[2].weight, tower.projection[2].bias))
+        zs.append(z.detach())
+    loss = O.triplet_loss(ys[0], ys[1], ys[2], margin)
     loss.backward()
-    grads = [dict(ref.named_parameters())[nm].grad for nm in NAMES]
-    return float(loss.item()), grads
+    grads = [dict(ref.named_parameters())[nm].grad.clone() for nm in NAMES]
+    return float(loss.item()), grads, torch.cat(zs)
+
+
+def check_gate_and_grads(tr, ref, batch, margin, tag):
+    """Shared gradient check of the fused step (see oracle_grads): returns the number of ReLU kink flips."""
+    ref_loss, raw_grads, z = oracle_grads(ref, batch, margin)
+    gate = tr.step_obj.relu_gate().cpu()
+    flips = gate != (z > 0)
+    n_flips = int(flips.sum())
+    assert n_flips <= 16, (tag, n_flips)                      # a handful of 3.1 M, not a systematic gate error
+    assert float(z[flips].abs().max()) <= KINK_BAND if n_flips else True, (tag, z[flips])
+    _, grads, _ = oracle_grads(ref, batch, margin, gate=gate)  # same gate on both sides
+    for nm, got, want_g, raw in zip(NAMES, tr.g_views, grads, raw_grads):
+        assert rel_err(got, want_g) < 1e-3, (tag, nm, rel_err(got, want_g))
+        assert rel_err(got, raw) < 5e-3 * max(1, n_flips), (tag, nm, rel_err(got, raw), n_flips)  # never far off the raw one
+    return ref_loss, n_flips
 
 
 @pytest.mark.parametrize("shape", ["U", "Z"])
@@ -76,7 +120,7 @@ def test_fused_step_configs1_vs_oracle(tt, precision, shape):
     tr._fwd_bwd()
     torch.cuda.synchronize()
     ref = oracle_twin(m, P, O.VOCAB)
-    ref_loss, ref_grads = oracle_grads(ref, batch, margin)
+    ref_loss, n_flips = check_gate_and_grads(tr, ref, batch, margin, (precision, shape))
     got_loss = float(tr.loss_view.item())
     assert abs(got_loss - ref_loss) <= 1e-4 * abs(ref_loss), (got_loss, ref_loss)
     # pooled + normalised rows, q | p | n
@@ -85,8 +129,7 @@ def test_fused_step_configs1_vs_oracle(tt, precision, shape):
                       O.pooled_normalised(ref.document_tower.table, batch.p_ids, batch.p_mask),
                       O.pooled_normalised(ref.document_tower.table, batch.n_ids, batch.n_mask)])
     assert row_rel(xhat, want) < 1e-4
-    for nm, got, want_g in zip(NAMES, tr.g_views, ref_grads):
-        assert rel_err(got, want_g) < 1e-3, (nm, rel_err(got, want_g))
+    print(f"configs[1] {precision} {shape}: {n_flips} ReLU kink flips of {3 * B * P}")
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -106,10 +149,9 @@ def test_fused_step_configs2_trainable_table_vs_oracle(tt, precision):
     torch.cuda.synchronize()
     first = [g.clone() for g in tr.table_grads]
     ref = oracle_twin(m, P, O.VOCAB, train_table=True)
-    ref_loss, ref_grads = oracle_grads(ref, batch, margin)
+    ref_loss, n_flips = check_gate_and_grads(tr, ref, batch, margin, (precision, "configs2"))
     assert abs(float(tr.loss_view.item()) - ref_loss) <= 1e-4 * abs(ref_loss)
-    for nm, got, want_g in zip(NAMES, tr.g_views, ref_grads):
-        assert rel_err(got, want_g) < 1e-3, (nm, rel_err(got, want_g))
+    # (ref's parameter .grad now hold the gradients taken through the device's gate, tables included)
     for got, tower in zip(tr.table_grads, (ref.query_tower, ref.document_tower)):
         assert rel_err(got, tower.table.grad) < 1e-3
         untouched = tower.table.grad.abs().sum(1) == 0

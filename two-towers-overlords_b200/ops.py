@@ -257,12 +257,27 @@ class TripletStep:
         self._keep.append(tokens)
         return len(self.slots) - 1
 
-    def pooled_rows(self) -> torch.Tensor:
-        """xhat [3B,H] fp32 of the last run, rows q | p | n: the first carve of the step workspace
-        (carve_step_ws in csrc/tt_api.cu).  Read-only view for the parity tests."""
-        B, _, _, H = self.shape[:4]
+    def _views(self) -> dict:
+        """fp32 activations of the last run inside the step workspace, rows q | p | n (the leading carves of
+        carve_step_ws in csrc/tt_api.cu: 256-byte aligned, in this order).  Read-only views for the parity tests."""
+        B, _, _, H, P = self.shape[:5]
+        R = 3 * B
         assert self.ws.data_ptr() % 256 == 0
-        return self.ws[: 3 * B * H * 4].view(torch.float32).view(3 * B, H)
+        out, off = {}, 0
+        for name, rows, cols in (("xhat", R, H), ("cnt", R, 1), ("nrm", R, 1), ("h", R, P), ("y", R, P),
+                                 ("stats", B, 8), ("dy", R, P)):
+            off = (off + 255) // 256 * 256
+            out[name] = self.ws[off: off + rows * cols * 4].view(torch.float32).view(rows, cols)
+            off += rows * cols * 4
+        return out
+
+    def pooled_rows(self) -> torch.Tensor:
+        """xhat [3B,H]: pooled + L2-normalised rows of the last run."""
+        return self._views()["xhat"]
+
+    def relu_gate(self) -> torch.Tensor:
+        """bool [3B,P]: which hidden units the last run treated as active (h > 0) — the ReLU gate of its backward."""
+        return self._views()["h"] > 0
 
     def run(self, slot: int = 0, phases: int = 0):
         """phases: 0 = whole step, 1 = pooled gather only (TT_STEP_FRONT), 2 = the rest (TT_STEP_BACK)."""
