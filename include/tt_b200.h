@@ -161,6 +161,16 @@ typedef struct tt_step_args {
   int phases;        /* 0 = whole step; TT_STEP_FRONT = pooled gather only (reads tokens + tables, not the
                         projection weights, so it may overlap the previous step's parameter exchange);
                         TT_STEP_BACK = everything after it, on the same workspace                             */
+  /* optional optimiser (training.py:51 `optimizer.step()`; adam_param NULL = gradients only): torch.optim.Adam
+   * arithmetic on ONE flat fp32 parameter buffer of adam_n elements.  The 8 projection tensors above must be
+   * slices of adam_param, and their gradients slices of adam_grad, at equal 16-byte aligned offsets; exp_avg /
+   * exp_avg_sq are flat buffers of the same length.  adam_state: 4 doubles as for tt_adam_step_dev, advanced once
+   * per call that has TT_STEP_BACK.  With the tensor-core precisions the update runs in the tail of the step's
+   * persistent chain kernel (no extra launch); otherwise it is launched after the step.                        */
+  double* adam_state;
+  float *adam_param, *adam_grad, *adam_exp_avg, *adam_exp_avg_sq;
+  size_t adam_n;
+  float adam_lr, adam_beta1, adam_beta2, adam_eps;
 } tt_step_args;
 #define TT_STEP_FRONT 1
 #define TT_STEP_BACK 2

@@ -151,8 +151,13 @@ def test_fused_step_configs2_trainable_table_vs_oracle(tt, precision):
     ref = oracle_twin(m, P, O.VOCAB, train_table=True)
     ref_loss, n_flips = check_gate_and_grads(tr, ref, batch, margin, (precision, "configs2"))
     assert abs(float(tr.loss_view.item()) - ref_loss) <= 1e-4 * abs(ref_loss)
-    # (ref's parameter .grad now hold the gradients taken through the device's gate, tables included)
-    for got, tower in zip(tr.table_grads, (ref.query_tower, ref.document_tower)):
+    # Table gradients: rows named by tens of thousands of tokens (Zipf heads: 74 k terms in one row here) are long
+    # sums of random signs, where the fp32 CPU oracle ITSELF is 1.3e-3 off float64 (sequential index_add) while the
+    # device's fixed-order split sums are 3e-4 off (scripts/diag_table_grad.py) — so the truth for this D2 extension
+    # is float64 autograd through nn.Embedding, differentiated through the device's ReLU gate like the rest.
+    ref64 = oracle_twin(m, P, O.VOCAB, train_table=True).double()
+    oracle_grads(ref64, batch, margin, gate=tr.step_obj.relu_gate().cpu())
+    for got, tower in zip(tr.table_grads, (ref64.query_tower, ref64.document_tower)):
         assert rel_err(got, tower.table.grad) < 1e-3
         untouched = tower.table.grad.abs().sum(1) == 0
         assert float(got.cpu()[untouched].abs().max()) == 0.0  # rows no token named stay exactly zero

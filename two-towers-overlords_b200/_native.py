@@ -60,6 +60,10 @@ class StepArgs(ctypes.Structure):
         ("precision", c_int),
         ("ws", c_void_p), ("ws_bytes", c_size_t),
         ("phases", c_int),
+        ("adam_state", c_void_p),
+        ("adam_param", c_void_p), ("adam_grad", c_void_p), ("adam_exp_avg", c_void_p), ("adam_exp_avg_sq", c_void_p),
+        ("adam_n", c_size_t),
+        ("adam_lr", c_float), ("adam_beta1", c_float), ("adam_beta2", c_float), ("adam_eps", c_float),
     ]
 
 

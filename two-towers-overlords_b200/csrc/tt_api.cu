@@ -203,6 +203,10 @@ static size_t carve_step_ws(char* base, int B, int Lq, int Ld, int H, int P, int
   return (size_t)(p - base) + 256;
 }
 
+extern "C" int tt_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                                float beta1, float beta2, float eps, double* state, float grad_scale,
+                                tt_stream_t stream);
+
 extern "C" size_t tt_step_ws_bytes(int B, int Lq, int Ld, int H, int P, int vocab, int precision, int train_table) {
   return carve_step_ws(nullptr, B, Lq, Ld, H, P, vocab, precision, train_table, nullptr);
 }
@@ -236,6 +240,7 @@ extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
   pp.err = a->err_flag;
 
   float* dxhat = train_table ? w.dxhat : nullptr;
+  bool adam_done = false;
   TT_REQUIRE(a->phases >= 0 && a->phases <= (TT_STEP_FRONT | TT_STEP_BACK), "tt_triplet_step: bad phases %d", a->phases);
   const bool front = a->phases == 0 || (a->phases & TT_STEP_FRONT), back = a->phases == 0 || (a->phases & TT_STEP_BACK);
   if (a->precision == TT_PREC_FP32) {
@@ -278,8 +283,20 @@ extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
     s.n_split = (a->precision == TT_PREC_BF16X3) ? 3 : 1;
     s.ws = w.mma_ws; s.ws_bytes = w.mma_ws_bytes;
     s.phases = a->phases;
+    if (a->adam_param && chain_enabled()) {  // the optimiser rides in the tail of the persistent chain kernel
+      s.adam = FusedAdam{a->adam_state, a->adam_param, a->adam_grad, a->adam_exp_avg, a->adam_exp_avg_sq, a->adam_n,
+                         a->adam_lr, a->adam_beta1, a->adam_beta2, a->adam_eps};
+      adam_done = true;
+    }
     if ((rc = step_sm100(s, st))) return rc;
     if (!back) return 0;
+  }
+  if (a->adam_param && !adam_done) {
+    TT_REQUIRE(a->adam_state && a->adam_grad && a->adam_exp_avg && a->adam_exp_avg_sq,
+               "tt_triplet_step: the optimiser needs state, grad and both moments");
+    if ((rc = tt_adam_step_dev(a->adam_param, a->adam_grad, a->adam_exp_avg, a->adam_exp_avg_sq, a->adam_n, a->adam_lr,
+                               a->adam_beta1, a->adam_beta2, a->adam_eps, a->adam_state, 1.f, stream)))
+      return rc;
   }
   // 6. table gradients (D2 extension)
   if (train_table) {

@@ -16,13 +16,13 @@
 #include "tt_ptx.cuh"
 #include "tt_simt.cuh"
 #include "tt_sm100.cuh"
+#include "tt_step_ws.cuh"
 #include "tt_tma.cuh"
 
 namespace tt {
 
 namespace {
 
-using bf16 = __nv_bfloat16;
 using namespace ptx;
 
 constexpr int BM = 128, BN = 128, BK = 64;
@@ -487,8 +487,6 @@ int transpose_pair(const bf16* hi, const bf16* lo, int R, int C, bf16* thi, bf16
   return 0;
 }
 
-inline int round64(int x) { return (x + 63) / 64 * 64; }
-
 // ---- workspace of one tower pass (standalone tt_encode_fwd / tt_encode_bwd) --------------------------------
 struct MlpWs {
   bf16 *x_hi, *x_lo, *x_lo2, *xt_hi, *xt_lo;  // [M,H], [H,ldm]
@@ -604,52 +602,6 @@ int mlp_bwd_sm100(const float* dy, const float* x, const float* h, const float* 
 // whole triplet step on the tensor cores: rows [0,B) = queries (query tower), rows [B,3B) = positives | negatives
 // (document tower).  Every GEMM launch carries both towers as two problem groups.
 // ================================================================================================================
-namespace {
-
-struct StepWs {
-  int ldt, dcol;  // transposed buffers: query rows at columns [0,B), document rows at [dcol, dcol+2B)
-  bf16 *x_hi, *x_lo, *x_lo2, *xt_hi, *xt_lo;  // [3B,H], [H,ldt]
-  bf16 *h_hi, *h_lo, *ht_hi, *ht_lo;        // [3B,P], [P,ldt]
-  bf16 *dy_hi, *dy_lo, *dyt_hi, *dyt_lo;    // [3B,P], [P,ldt]
-  bf16 *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;    // [3B,P], [P,ldt]
-  bf16 *w1_hi[2], *w1_lo[2], *w1_lo2[2], *w1t_hi[2], *w1t_lo[2];  // per tower: [P,H], [H,P]
-  bf16 *w2_hi[2], *w2_lo[2], *w2t_hi[2], *w2t_lo[2];  // per tower: [P,P], [P,P]
-  float *dz1, *partial, *partial2, *colsum, *colsum2, *loss_scratch;
-};
-
-size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out) {
-  char* p = base;
-  StepWs w{};
-  w.dcol = round64(B);
-  w.ldt = w.dcol + round64(2 * B);
-  const size_t R = (size_t)3 * B;
-  w.x_hi = ws_take<bf16>(p, R * H); w.x_lo = ws_take<bf16>(p, R * H); w.x_lo2 = ws_take<bf16>(p, R * H);
-  w.xt_hi = ws_take<bf16>(p, (size_t)H * w.ldt); w.xt_lo = ws_take<bf16>(p, (size_t)H * w.ldt);
-  w.h_hi = ws_take<bf16>(p, R * P); w.h_lo = ws_take<bf16>(p, R * P);
-  w.ht_hi = ws_take<bf16>(p, (size_t)P * w.ldt); w.ht_lo = ws_take<bf16>(p, (size_t)P * w.ldt);
-  w.dy_hi = ws_take<bf16>(p, R * P); w.dy_lo = ws_take<bf16>(p, R * P);
-  w.dyt_hi = ws_take<bf16>(p, (size_t)P * w.ldt); w.dyt_lo = ws_take<bf16>(p, (size_t)P * w.ldt);
-  w.dz_hi = ws_take<bf16>(p, R * P); w.dz_lo = ws_take<bf16>(p, R * P);
-  w.dzt_hi = ws_take<bf16>(p, (size_t)P * w.ldt); w.dzt_lo = ws_take<bf16>(p, (size_t)P * w.ldt);
-  for (int t = 0; t < 2; ++t) {
-    w.w1_hi[t] = ws_take<bf16>(p, (size_t)P * H); w.w1_lo[t] = ws_take<bf16>(p, (size_t)P * H);
-    w.w1_lo2[t] = ws_take<bf16>(p, (size_t)P * H);
-    w.w1t_hi[t] = ws_take<bf16>(p, (size_t)P * H); w.w1t_lo[t] = ws_take<bf16>(p, (size_t)P * H);
-    w.w2_hi[t] = ws_take<bf16>(p, (size_t)P * P); w.w2_lo[t] = ws_take<bf16>(p, (size_t)P * P);
-    w.w2t_hi[t] = ws_take<bf16>(p, (size_t)P * P); w.w2t_lo[t] = ws_take<bf16>(p, (size_t)P * P);
-  }
-  w.dz1 = ws_take<float>(p, R * P);
-  w.partial = ws_take<float>(p, (size_t)2 * 32 * P * max(P, H));
-  w.partial2 = ws_take<float>(p, (size_t)2 * 32 * P * P);  // dW2's split-K sums: it runs beside the dW1 branch
-  w.colsum = ws_take<float>(p, (size_t)2 * kColsumSlices * P);
-  w.colsum2 = ws_take<float>(p, (size_t)2 * kColsumSlices * P);
-  w.loss_scratch = ws_take<float>(p, (size_t)(B + 3) / 4 + 8);
-  (void)train_table;
-  if (out) *out = w;
-  return (size_t)(p - base) + 256;
-}
-
-}  // namespace
 
 size_t step_sm100_ws_bytes(int B, int H, int P, int train_table) { return carve_step(nullptr, B, H, P, train_table, nullptr); }
 
@@ -712,6 +664,7 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
     if ((rc = transpose_pair(w.x_hi, w.x_lo, 3 * B, H, w.xt_hi, w.xt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
   }
   if (!back) return 0;
+  if (chain_enabled()) return chain_sm100(s, st);
   // 2. weights of both towers -> bf16 terms (+ transposes for the backward contractions), one launch
   {
     SplitJob jobs[4];

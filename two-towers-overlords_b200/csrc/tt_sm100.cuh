@@ -12,6 +12,13 @@ int mlp_bwd_sm100(const float* dy, const float* x, const float* h, const float* 
                   int P, float* dW1, float* db1, float* dW2, float* db2, float* dx, int accumulate, int precision,
                   void* ws, size_t ws_bytes, cudaStream_t st);
 
+struct FusedAdam {  // optional optimiser in the tail of the persistent chain kernel (param == nullptr: gradients only)
+  double* state;
+  float *param, *grad, *exp_avg, *exp_avg_sq;
+  size_t n;
+  float lr, beta1, beta2, eps;
+};
+
 struct StepSm100 {
   PoolParams pool;  // xhat/cnt/nrm/err filled by the caller; split outputs filled by step_sm100
   int table_dtype;
@@ -26,9 +33,13 @@ struct StepSm100 {
   void* ws;
   size_t ws_bytes;
   int phases;                 // 0 / TT_STEP_FRONT | TT_STEP_BACK
+  FusedAdam adam;
 };
 size_t step_sm100_ws_bytes(int B, int H, int P, int train_table);
 int step_sm100(const StepSm100& s, cudaStream_t st);
+// persistent chain kernel (tt_chain_sm100.cu): everything of the step after the pooled gather in ONE launch
+bool chain_enabled();  // TT_CHAIN=0 selects the per-kernel chain
+int chain_sm100(const StepSm100& s, cudaStream_t st);
 
 size_t scan_sm100_ws_bytes(int Q, long long N, int P, int k);
 int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void* Db, int Q, long long N, int P, int k,

@@ -210,6 +210,7 @@ class TripletStep:
         self.args = N.StepArgs()
         self.slots = []
         self._keep = []
+        self._adam = None
 
     def bind(self, tokens, tables, params, grads, margin, inv_batch, grad_scale=1.0, table_grads=None):
         """tokens = (q_ids,q_mask,p_ids,p_mask,n_ids,n_mask) CUDA tensors; tables = (table_q, table_d);
@@ -239,6 +240,7 @@ class TripletStep:
         else:
             a.dtable_q, a.dtable_d = None, None
         a.precision, a.ws, a.ws_bytes = self.prec, N.ptr(self.ws), self.ws_bytes
+        a.adam_param = None
         self.slots = [a]
         self._keep = [(tokens, tables, params, grads, table_grads)]
 
@@ -264,8 +266,11 @@ class TripletStep:
         R = 3 * B
         assert self.ws.data_ptr() % 256 == 0
         out, off = {}, 0
-        for name, rows, cols in (("xhat", R, H), ("cnt", R, 1), ("nrm", R, 1), ("h", R, P), ("y", R, P),
-                                 ("stats", B, 8), ("dy", R, P)):
+        names = [("xhat", R, H), ("cnt", R, 1), ("nrm", R, 1), ("h", R, P), ("y", R, P), ("stats", B, 8), ("dy", R, P),
+                 ("dz1", R, P)]
+        if self.train_table:
+            names += [("dxhat", R, H), ("g", R, H)]
+        for name, rows, cols in names:
             off = (off + 255) // 256 * 256
             out[name] = self.ws[off: off + rows * cols * 4].view(torch.float32).view(rows, cols)
             off += rows * cols * 4
@@ -279,12 +284,27 @@ class TripletStep:
         """bool [3B,P]: which hidden units the last run treated as active (h > 0) — the ReLU gate of its backward."""
         return self._views()["h"] > 0
 
-    def run(self, slot: int = 0, phases: int = 0):
-        """phases: 0 = whole step, 1 = pooled gather only (TT_STEP_FRONT), 2 = the rest (TT_STEP_BACK)."""
+    def bind_adam(self, state, param, grad, exp_avg, exp_avg_sq, lr, betas, eps):
+        """Optional optimiser inside the step call (tt_step_args.adam_*): flat fp32 buffers the 8 projection tensors
+        and their gradients are slices of.  Only run(..., optimise=True) applies it."""
+        self._adam = (N.ptr(state), N.ptr(param), N.ptr(grad), N.ptr(exp_avg), N.ptr(exp_avg_sq), param.numel(),
+                      float(lr), float(betas[0]), float(betas[1]), float(eps))
+        self._keep.append((state, param, grad, exp_avg, exp_avg_sq))
+
+    def run(self, slot: int = 0, phases: int = 0, optimise: bool = False):
+        """phases: 0 = whole step, 1 = pooled gather only (TT_STEP_FRONT), 2 = the rest (TT_STEP_BACK).
+        optimise: also apply the optimiser bound with bind_adam() (gradients only otherwise)."""
         a = self.slots[slot]
         a.phases = int(phases)
+        if optimise and phases != 1:
+            assert self._adam is not None, "run(optimise=True) needs bind_adam() first"
+            (a.adam_state, a.adam_param, a.adam_grad, a.adam_exp_avg, a.adam_exp_avg_sq, a.adam_n, a.adam_lr,
+             a.adam_beta1, a.adam_beta2, a.adam_eps) = self._adam
+        else:
+            a.adam_param = None
         N.check(self.lib.tt_triplet_step(ctypes.byref(a), N.stream()), "tt_triplet_step")
         a.phases = 0
+        a.adam_param = None
         return self.loss
 
 

@@ -221,6 +221,11 @@ class FusedTrainer:
                     self.g_views, self.margin, 1.0 / (batch_size * world_size), 1.0, self.table_grads)
             for toks in self.tok_slots[1:]:
                 so.add_tokens(toks)
+            if self.exchange == "none" and self.world == 1:
+                # single GPU: torch.optim.Adam rides inside the step call (the tail of the persistent chain kernel
+                # with the tensor-core precisions; a launch after the step otherwise)
+                so.bind_adam(self.adam_state, self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.lr,
+                             self.betas, self.eps)
             self.step_objs.append(so)
         self.step_obj = self.step_objs[0]
         self.use_graph = use_graph
@@ -283,8 +288,8 @@ class FusedTrainer:
                                                    n.input_ids, n.attention_mask)):
             dst.copy_(src, non_blocking=True)
 
-    def _fwd_bwd(self, slot: int = 0, phases: int = 0, parity: int = 0):
-        self.step_objs[parity].run(slot, phases)
+    def _fwd_bwd(self, slot: int = 0, phases: int = 0, parity: int = 0, optimise: bool = False):
+        self.step_objs[parity].run(slot, phases, optimise=optimise)
 
     def _exchange(self):
         """The fused reduce-scatter / Adam / all-gather kernel (tt_dp_reduce_adam) on the current stream."""
@@ -300,11 +305,10 @@ class FusedTrainer:
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
                 self._fwd_bwd(next_slot, 1, parity ^ 1)
-        self._fwd_bwd(slot, 2, parity)
+        fused_opt = self.xchg is None and self.world == 1
+        self._fwd_bwd(slot, 2, parity, optimise=fused_opt)
         if self.xchg is not None:
             self._exchange()
-        elif self.world == 1:
-            self._optimizer()
         if next_slot is not None:
             cur.wait_stream(self.side)
 
