@@ -171,6 +171,11 @@ typedef struct tt_step_args {
   float *adam_param, *adam_grad, *adam_exp_avg, *adam_exp_avg_sq;
   size_t adam_n;
   float adam_lr, adam_beta1, adam_beta2, adam_eps;
+  int chain;         /* tensor-core precisions: how everything after the pooled gather is launched.
+                        1 = ONE persistent kernel (both layers, loss in the layer-2 epilogue, backward, bias sums,
+                        gradient reduction, optimiser); 2 = one kernel per contraction (small kernels a concurrent
+                        look-ahead gather can slip between); 0 = library default: TT_CHAIN env (1 / 0 = per-kernel),
+                        else 1.  Keep the same choice for the TT_STEP_FRONT and TT_STEP_BACK calls of one step.   */
 } tt_step_args;
 #define TT_STEP_FRONT 1
 #define TT_STEP_BACK 2
@@ -305,6 +310,11 @@ int tt_assemble_triplets(const tt_token_bank* qbank, const tt_token_bank* dbank,
  * launch with CUDA events: GB/s = bytes * iters / seconds.  This is the ceiling of the pooled gather, whose token
  * tables stay resident in L2 (the reference's counterpart is nn.Embedding inside backend/model.py:51-52).
  * ctas_per_sm <= 0 selects 8 (x 256 threads).  sink: 4 writable bytes. */
+/* Diagnostics / parity tests: device address of a named internal buffer of a tensor-core step workspace:
+ * "trace" (task timeline of the persistent chain kernel after a TT_CHAIN_TRACE=1 step: [160][64] pairs of
+ * {task << 2 | kind, globaltimer ns}), "h_hi" / "h_lo" / "dy_hi" / "dy_lo" (bf16 terms [3B,P], rows q | p | n). */
+int tt_debug_step_buffer(void* ws, int B, int Lq, int Ld, int H, int P, int vocab, int precision, int train_table,
+                         const char* name, void** ptr);
 int tt_ubench_l2_read(const void* buf, size_t bytes, int iters, int ctas_per_sm, void* sink, tt_stream_t stream);
 
 #ifdef __cplusplus

@@ -31,7 +31,7 @@ def run(B, P, precision, train_table, chain, shape="Z", iters=20):
     tr._fwd_bwd()
     torch.cuda.synchronize()
     v = tr.step_obj._views()
-    out = {"loss": tr.loss_view.clone(), "h": v["h"].clone(), "stats": v["stats"].clone(),
+    out = {"loss": tr.loss_view.clone(), "h": tr.step_obj.hidden().clone(), "stats": v["stats"].clone(),
            "grads": [g.clone() for g in tr.g_views]}
     if train_table:
         out["tables"] = [g.clone() for g in tr.table_grads]

@@ -6,6 +6,7 @@
 #include "tt_scan.cuh"
 #include "tt_simt.cuh"
 #include "tt_sm100.cuh"
+#include "tt_step_ws.cuh"
 
 namespace tt {
 
@@ -167,7 +168,7 @@ extern "C" int tt_encode_bwd(const float* dy, const float* x, const float* h, co
 // ------------------------------------------------------------------------------------------------
 // whole triplet step
 // ------------------------------------------------------------------------------------------------
-struct StepWs {
+struct ApiStepWs {
   float *xhat, *cnt, *nrm, *h, *y, *stats, *dy, *dz1, *dxhat, *g;
   void* pool_ws;
   size_t pool_ws_bytes;
@@ -176,10 +177,10 @@ struct StepWs {
 };
 
 static size_t carve_step_ws(char* base, int B, int Lq, int Ld, int H, int P, int vocab, int precision, int train_table,
-                            StepWs* out) {
+                            ApiStepWs* out) {
   char* p = base;
   const size_t R = (size_t)3 * B;
-  StepWs w{};
+  ApiStepWs w{};
   w.xhat = ws_take<float>(p, R * H);
   w.cnt = ws_take<float>(p, R);
   w.nrm = ws_take<float>(p, R);
@@ -211,6 +212,27 @@ extern "C" size_t tt_step_ws_bytes(int B, int Lq, int Ld, int H, int P, int voca
   return carve_step_ws(nullptr, B, Lq, Ld, H, P, vocab, precision, train_table, nullptr);
 }
 
+// Diagnostics and parity tests: device address of a named internal buffer of a tensor-core step workspace.
+//   "trace"  per-CTA task timeline of the last TT_CHAIN_TRACE=1 step: [160][64] x {task << 2 | kind, globaltimer ns}
+//   "h_hi" / "h_lo" / "dy_hi" / "dy_lo"  bf16 terms [3B, P] of the hidden activations / of dY (rows q | p | n)
+extern "C" int tt_debug_step_buffer(void* ws, int B, int Lq, int Ld, int H, int P, int vocab, int precision,
+                                    int train_table, const char* name, void** ptr) {
+  TT_REQUIRE(ws && name && ptr && precision != TT_PREC_FP32, "tt_debug_step_buffer: bad arguments");
+  ApiStepWs w;
+  carve_step_ws(reinterpret_cast<char*>(ws), B, Lq, Ld, H, P, vocab, precision, train_table, &w);
+  tt::StepWs m;
+  tt::carve_step(reinterpret_cast<char*>(w.mma_ws), B, H, P, train_table, &m);
+  void* out = nullptr;
+  if (!strcmp(name, "trace")) out = m.trace;
+  else if (!strcmp(name, "h_hi")) out = m.h_hi;
+  else if (!strcmp(name, "h_lo")) out = m.h_lo;
+  else if (!strcmp(name, "dy_hi")) out = m.dy_hi;
+  else if (!strcmp(name, "dy_lo")) out = m.dy_lo;
+  TT_REQUIRE(out != nullptr, "tt_debug_step_buffer: unknown buffer '%s'", name);
+  *ptr = out;
+  return 0;
+}
+
 extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
   TT_REQUIRE(a != nullptr, "tt_triplet_step: null args");
   const int B = a->B, H = a->H, P = a->P;
@@ -222,7 +244,7 @@ extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
   const size_t need = tt_step_ws_bytes(B, a->Lq, a->Ld, H, P, a->vocab, a->precision, train_table);
   TT_REQUIRE(a->ws && a->ws_bytes >= need, "tt_triplet_step: workspace too small (%zu < %zu)", a->ws_bytes, need);
   cudaStream_t st = as_stream(stream);
-  StepWs w;
+  ApiStepWs w;
   carve_step_ws(reinterpret_cast<char*>(a->ws), B, a->Lq, a->Ld, H, P, a->vocab, a->precision, train_table, &w);
 
   // 1. pooled gather for q | p | n rows
@@ -283,7 +305,9 @@ extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
     s.n_split = (a->precision == TT_PREC_BF16X3) ? 3 : 1;
     s.ws = w.mma_ws; s.ws_bytes = w.mma_ws_bytes;
     s.phases = a->phases;
-    if (a->adam_param && chain_enabled()) {  // the optimiser rides in the tail of the persistent chain kernel
+    TT_REQUIRE(a->chain >= 0 && a->chain <= 2, "tt_triplet_step: bad chain selector %d", a->chain);
+    s.chain = a->chain;
+    if (a->adam_param && (a->chain == 1 || (a->chain == 0 && chain_enabled()))) {  // the optimiser rides in the chain kernel's tail
       s.adam = FusedAdam{a->adam_state, a->adam_param, a->adam_grad, a->adam_exp_avg, a->adam_exp_avg_sq, a->adam_n,
                          a->adam_lr, a->adam_beta1, a->adam_beta2, a->adam_eps};
       adam_done = true;

@@ -39,35 +39,53 @@ constexpr int kAcc = 4;  // TMEM accumulator ring
 constexpr int kEpiThreads = 256;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
-constexpr int kStagingBytes = 2 * 8 * 64 * 4 /*column sums*/ + 2 * 32 * 33 * 2 /*split tile*/ + 64;
+constexpr int kSplitPad = 66;  // bf16 elements per row of a transposed 64 x 64 staging tile
+// Per-epilogue-warp row staging: a thread owns a tile row (TMEM lane), so direct stores would scatter 16-byte pieces
+// over 32 rows per instruction; instead the warp parks a [32 rows x 16 | 32 columns] block in shared memory and writes
+// it out with whole sectors / lines per row.  The split phase's transpose tiles overlay the same bytes.
+constexpr int kRowStage = 3072;   // per warp: 2 x 1536 (two bf16 blocks of 16 columns) or 2560 (fp32, 16 columns)
+constexpr int kTermPitch = 48;    // bytes per row of a 16-column bf16 block (32 B + pad: conflict-free 16 B accesses)
+constexpr int kTermBlock = 32 * kTermPitch;
+constexpr int kF32Pitch = 80;     // bytes per row of a 16-column fp32 block (64 B + pad)
+constexpr int kCsBytes = 2 * 8 * 64 * 4;
+constexpr int kStagingBytes = kCsBytes /*column sums*/ + 8 * kRowStage /*row staging | split tiles*/ + 64;
+static_assert(2 * 64 * kSplitPad * 2 <= 8 * kRowStage, "split tiles overlay the row staging");
 constexpr size_t chain_smem(int stages) { return (size_t)stages * kStageBytes + 1024 + 256 + kStagingBytes; }
 constexpr float kCosEps = 1e-8f;  // torch.cosine_similarity eps (per-vector clamp), backend/model.py:134
 constexpr long long kSpinLimit = 4000000000ll;
 
-enum { T_S = 0, T_F1, T_F2L, T_DZ, T_DX, T_DW2, T_DW1, T_G, T_COUNT };
+enum { T_S = 0, T_T, T_F1, T_F2L, T_DZ, T_DX, T_DW2, T_DW1, T_G, T_COUNT };
 
 struct TowerMaps {  // K-major bf16 operand terms of one tower (box 128 rows x 64 k)
   CUtensorMap x[3], w1[3];   // F1:  [rows,H] x [P,H]
-  CUtensorMap h[2], w2[2];   // F2:  [rows,P] x [P,P]
+  CUtensorMap h[2], w2[2];   // F2:  [rows,P] x [P,P]   (w2: boxes of 64 rows — the loss tiles are 64 columns wide)
   CUtensorMap dy[2], w2t[2];  // DZ:  [rows,P] x [P,P]^T
   CUtensorMap dyt[2], ht[2];  // DW2: [P,rows] x [P,rows]
   CUtensorMap dzt[2], xt[2];  // DW1: [P,rows] x [H,rows]
   CUtensorMap dz[2], w1t[2];  // DX:  [rows,P] x [H,P]
 };
 
-struct SplitJobC {
+struct SplitJobC {  // fp32 [R, C] dense -> bf16 terms hi/lo[/lo2] [R, C] and (optional) transposed hi/lo [C, R]
   const float* X;
   bf16 *hi, *lo, *lo2, *thi, *tlo;
-  int R, C, ldt, tile0, tiles_c;
+  int R, C;
+  int f4_0;    // first float4 of this matrix in the flat pass over all jobs
+  int t64_0;   // first 64 x 64 tile of this matrix in the transpose pass (-1: no transposed copy)
+  int tiles_c;
 };
 
 struct alignas(64) ChainParams {
   TowerMaps tm[2];
-  int B, H, P, RTB, NC, NCH, ldt, dcol;
+  int B, H, P, RTB, NC, NCH, NCF, ldt, dcol;  // NCF: 64-column tiles of the fused layer-2 / loss phase
   int pairs, terms, pairs1, terms1;
   int kcb, nch[2], kbt[2];
   int off[T_COUNT + 1];
-  int stages, n_sj, n_split_tiles;
+  int stages, n_sj, n_split_f4, n_split_f4_w1, n_split_t64;
+  int nS;        // tasks of the S, T and G phases: one per CTA
+  int krot;      // rotate the k-block order per CTA (tuning hook TT_CHAIN_KROT)
+  int use_pdl;   // launched as a programmatic dependent of the pooled gather: wait for it before touching x
+  const bf16 *x_hi, *x_lo;
+  bf16 *xt_hi, *xt_lo;
   SplitJobC sj[6];
   float margin, inv_batch, grad_scale;
   const float *b1[2], *b2[2];
@@ -75,13 +93,15 @@ struct alignas(64) ChainParams {
   bf16 *h_hi, *h_lo, *ht_hi, *ht_lo, *dy_hi, *dy_lo, *dyt_hi, *dyt_lo, *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;
   float *part2, *part1;
   float *dW1[2], *db1[2], *dW2[2], *db2[2];
-  float *stat_part, *cs1, *cs2, *hinge_part;
+  float *stat_part, *cs1, *cs2, *hinge_part, *ybuf;
   unsigned* ctr;
+  int n_counters;
   // optional fused optimiser: torch.optim.Adam on the flat parameter buffer the 8 tensors are slices of
   double* adam_state;  // {t, beta1^t, beta2^t, -}: advanced once per launch (by the first task), read by the tail
   float *adam_p, *adam_g, *adam_m, *adam_v;
   float lr, beta1, beta2, eps;
   unsigned total_signals;
+  unsigned long long* trace;  // nullable (TT_CHAIN_TRACE=1)
 };
 
 // ---- cross-CTA hand-off ------------------------------------------------------------------------------------
@@ -94,13 +114,22 @@ __device__ __forceinline__ void signal(unsigned* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Polls with relaxed loads (an acquire load invalidates the SM's L1 on every poll, which evicts the epilogue warps'
+// bias lines and register spills) and orders everything after the successful poll with one acquire fence.
 __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
-  if (ld_acquire(p) >= target) return;
-  const long long t0 = clock64();
-  while (ld_acquire(p) < target) {
-    __nanosleep(64);
-    if (clock64() - t0 > kSpinLimit) __trap();  // a protocol bug fails the launch instead of hanging the GPU
+  if (ld_relaxed(p) < target) {
+    const long long t0 = clock64();
+    while (ld_relaxed(p) < target) {
+      __nanosleep(32);
+      if (clock64() - t0 > kSpinLimit) __trap();  // a protocol bug fails the launch instead of hanging the GPU
+    }
   }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -133,8 +162,11 @@ __device__ __forceinline__ RowTile row_tile(const ChainParams& p, int u) {
 struct Sub {
   const CUtensorMap *a, *b;
   int terms, pairs, m0, n0, kb0, nkb;
+  int bn;  // MMA N = rows of the B box (128, or 64 for the loss tiles)
 };
-__device__ __forceinline__ int n_subs(int type) { return type == T_F2L ? 3 : ((type == T_S || type == T_G) ? 0 : 1); }
+__device__ __forceinline__ int n_subs(int type) {
+  return (type == T_S || type == T_T || type == T_G) ? 0 : 1;
+}
 
 __device__ __forceinline__ void dw_chunk(const ChainParams& p, int ci, int& t, int& j) {
   t = ci >= p.nch[0];
@@ -146,6 +178,7 @@ __device__ __forceinline__ Sub get_sub(const ChainParams& p, Task tk, int k) {
   s.terms = p.terms;
   s.pairs = p.pairs;
   s.kb0 = 0;
+  s.bn = BN;
   switch (tk.type) {
     case T_F1: {
       const RowTile rt = row_tile(p, tk.i / p.NC);
@@ -153,10 +186,11 @@ __device__ __forceinline__ Sub get_sub(const ChainParams& p, Task tk, int k) {
       s.terms = p.terms1; s.pairs = p.pairs1;
       s.m0 = rt.trow; s.n0 = (tk.i % p.NC) * BN; s.nkb = p.H / BK;
     } break;
-    case T_F2L: {
-      const int r = tk.i / p.NC, t = k != 0;
+    case T_F2L: {  // task = ((r, c), seg): layer 2 of 128 rows of one row group (q | p | n) x 64 columns
+      const int seg = tk.i % 3, rc = tk.i / 3, r = rc / p.NCF, t = seg != 0;
       s.a = p.tm[t].h; s.b = p.tm[t].w2;
-      s.m0 = (k == 2 ? p.B : 0) + r * BM; s.n0 = (tk.i % p.NC) * BN; s.nkb = p.P / BK;
+      s.m0 = (seg == 2 ? p.B : 0) + r * BM; s.n0 = (rc % p.NCF) * 64; s.nkb = p.P / BK;
+      s.bn = 64;
     } break;
     case T_DZ: {
       const RowTile rt = row_tile(p, tk.i / p.NC);
@@ -192,29 +226,32 @@ __device__ __forceinline__ unsigned* h_ready(const ChainParams& p) { return p.ct
 __device__ __forceinline__ unsigned* dy_ready(const ChainParams& p) { return p.ctr + 8 + 3 * p.RTB; }
 __device__ __forceinline__ unsigned* dz_ready(const ChainParams& p) { return p.ctr + 8 + 6 * p.RTB; }
 __device__ __forceinline__ unsigned* stat_ready(const ChainParams& p) { return p.ctr + 8 + 9 * p.RTB; }
+__device__ __forceinline__ unsigned* y_ready(const ChainParams& p) { return p.ctr + 8 + 10 * p.RTB; }  // [RTB * NCF]
 
 // every row tile [seg][r] that holds one of the batch rows [k0, k1) of tower t must have all NC column tiles done
-__device__ __forceinline__ void wait_rows(const ChainParams& p, const unsigned* ready, int t, int k0, int k1) {
+__device__ __forceinline__ void wait_rows(const ChainParams& p, const unsigned* ready, unsigned need, int t, int k0,
+                                          int k1) {
   if (t == 0) {
-    for (int r = k0 / BM; r <= (k1 - 1) / BM; ++r) wait_counter(ready + r, p.NC);
+    for (int r = k0 / BM; r <= (k1 - 1) / BM; ++r) wait_counter(ready + r, need);
     return;
   }
   if (k0 < p.B)
-    for (int r = k0 / BM; r <= (min(k1, p.B) - 1) / BM; ++r) wait_counter(ready + p.RTB + r, p.NC);
+    for (int r = k0 / BM; r <= (min(k1, p.B) - 1) / BM; ++r) wait_counter(ready + p.RTB + r, need);
   if (k1 > p.B)
-    for (int r = (max(k0, p.B) - p.B) / BM; r <= (k1 - p.B - 1) / BM; ++r) wait_counter(ready + 2 * p.RTB + r, p.NC);
+    for (int r = (max(k0, p.B) - p.B) / BM; r <= (k1 - p.B - 1) / BM; ++r) wait_counter(ready + 2 * p.RTB + r, need);
 }
 
 __device__ __forceinline__ void wait_deps(const ChainParams& p, Task tk) {
   switch (tk.type) {
-    case T_F1: wait_counter(p.ctr + 0, (unsigned)(p.off[T_F1] - p.off[T_S])); break;
+    case T_F1: wait_counter(p.ctr + 0, (unsigned)p.nS); break;
     case T_F2L: {
-      const int r = tk.i / p.NC;
-      for (int seg = 0; seg < 3; ++seg) wait_counter(h_ready(p) + seg * p.RTB + r, p.NC);
+      const int seg = tk.i % 3, r = tk.i / 3 / p.NCF;
+      wait_counter(p.ctr + 2, (unsigned)p.nS);  // second-layer weight terms (and transposes)
+      wait_counter(h_ready(p) + seg * p.RTB + r, p.NC);
     } break;
     case T_DZ: {
       const RowTile rt = row_tile(p, tk.i / p.NC);
-      wait_counter(dy_ready(p) + rt.seg * p.RTB + rt.r, p.NC);
+      wait_counter(dy_ready(p) + rt.seg * p.RTB + rt.r, p.NCF);
     } break;
     case T_DX: {
       const RowTile rt = row_tile(p, tk.i / p.NCH);
@@ -226,7 +263,12 @@ __device__ __forceinline__ void wait_deps(const ChainParams& p, Task tk) {
       int t, j;
       dw_chunk(p, tk.i / nt_, t, j);
       const int k0 = j * p.kcb * BK, k1 = min(k0 + p.kcb * BK, t ? 2 * p.B : p.B);
-      wait_rows(p, tk.type == T_DW2 ? dy_ready(p) : dz_ready(p), t, k0, k1);
+      if (tk.type == T_DW2) {
+        wait_rows(p, dy_ready(p), p.NCF, t, k0, k1);
+      } else {
+        wait_counter(p.ctr + 3, (unsigned)p.nS);  // transposed xhat terms
+        wait_rows(p, dz_ready(p), p.NC, t, k0, k1);
+      }
     } break;
     default: break;
   }
@@ -264,26 +306,49 @@ __device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
   for (int j = 0; j < 4; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-// (hi, lo) bf16 terms of 16 values: row-major [.., ld] at `o` and / or transposed [n + j][tcol]
-__device__ __forceinline__ void store_terms(const float (&v)[16], bf16* c_hi, bf16* c_lo, size_t o, bf16* t_hi,
-                                            bf16* t_lo, int n, int ldt, int tcol) {
-  alignas(16) bf16 hi[16], lo[16];
+__device__ __forceinline__ void split16(const float (&v)[16], bf16 (&hi)[16], bf16 (&lo)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) split_bf16(v[j], hi[j], lo[j]);
-  if (c_hi) {
-    uint4* dh = reinterpret_cast<uint4*>(c_hi + o);
-    uint4* dl = reinterpret_cast<uint4*>(c_lo + o);
-    dh[0] = reinterpret_cast<const uint4*>(hi)[0];
-    dh[1] = reinterpret_cast<const uint4*>(hi)[1];
-    dl[0] = reinterpret_cast<const uint4*>(lo)[0];
-    dl[1] = reinterpret_cast<const uint4*>(lo)[1];
-  }
-  if (t_hi) {  // lanes hold consecutive rows: each store instruction is one coalesced 64 B run per column
+}
+// transposed copy [n + j][tcol]: lanes hold consecutive rows, so each store instruction is one 64 B run per column
+__device__ __forceinline__ void store_t(const bf16 (&hi)[16], const bf16 (&lo)[16], bf16* t_hi, bf16* t_lo, int n, int ldt,
+                                        int tcol) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      t_hi[(size_t)(n + j) * ldt + tcol] = hi[j];
-      t_lo[(size_t)(n + j) * ldt + tcol] = lo[j];
-    }
+  for (int j = 0; j < 16; ++j) {
+    t_hi[(size_t)(n + j) * ldt + tcol] = hi[j];
+    t_lo[(size_t)(n + j) * ldt + tcol] = lo[j];
+  }
+}
+// this lane's 16 bf16 (32 B) -> row `lane` of a staged block
+__device__ __forceinline__ void stage16(uint8_t* blk, int lane, const bf16 (&x)[16]) {
+  uint4* d = reinterpret_cast<uint4*>(blk + lane * kTermPitch);
+  d[0] = reinterpret_cast<const uint4*>(x)[0];
+  d[1] = reinterpret_cast<const uint4*>(x)[1];
+}
+// staged block [32 rows][16 bf16] -> g[(row0 + r) * ld + n ..], rows r < vr: two lanes per row, 16 rows per instruction
+__device__ __forceinline__ void flush16(const uint8_t* blk, int lane, bf16* g, size_t row0, int n, int ld, int vr) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int r = it * 16 + (lane >> 1), sg = lane & 1;
+    if (r < vr)
+      *reinterpret_cast<uint4*>(g + (row0 + r) * ld + n + sg * 8) =
+          *reinterpret_cast<const uint4*>(blk + r * kTermPitch + sg * 16);
+  }
+}
+// fp32: this lane's 16 values -> row `lane` of a staged [32][16] block
+__device__ __forceinline__ void stage_f32(uint8_t* blk, int lane, const float (&v)[16]) {
+  float4* d = reinterpret_cast<float4*>(blk + lane * kF32Pitch);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// staged [32 rows][16 fp32] -> g[(row0 + r) * ld + n ..]: four lanes per row (two whole sectors), eight rows per instruction
+__device__ __forceinline__ void flush_f32(const uint8_t* blk, int lane, float* g, size_t row0, int n, size_t ld, int vr) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), sg = lane & 3;
+    if (r < vr)
+      *reinterpret_cast<float4*>(g + (row0 + r) * ld + n + sg * 4) =
+          *reinterpret_cast<const float4*>(blk + r * kF32Pitch + sg * 16);
   }
 }
 
@@ -291,12 +356,26 @@ struct EpiCtx {
   uint32_t tmem_base;
   uint64_t *acc_full, *acc_empty;
   float* cs_s;  // [2][8][64]
-  bf16* sp_s;   // [2][32][33]
+  bf16* sp_s;   // [2][64][kSplitPad]
   float* hs_s;  // [4]
+  uint8_t* rs;  // this warp's row staging (kRowStage bytes)
   int we, q, hf, lane, tid;  // epilogue warp 0..7, TMEM lane quarter, column half, lane, epilogue thread 0..255
   int ab;
   uint32_t aph;
+  unsigned long long* trace;  // this CTA's timeline slots (nullable)
+  int tslot, tidx;
 };
+
+// timeline event of the current task: kind 0 = start, 1 = end, 2 = accumulators ready, 3 = sibling sums arrived
+__device__ __forceinline__ void trace_ev(EpiCtx& e, int kind) {
+  if (e.trace && e.tid == 0 && e.tslot < kTraceSlots) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    e.trace[e.tslot * 2] = ((unsigned long long)e.tidx << 2) | (unsigned long long)kind;
+    e.trace[e.tslot * 2 + 1] = t;
+    ++e.tslot;
+  }
+}
 
 __device__ __forceinline__ uint32_t acc_addr(const EpiCtx& e, int buf, int chunk) {
   return e.tmem_base + ((uint32_t)(e.q * 32) << 16) + (uint32_t)(buf * BN + e.hf * 64 + chunk * 16);
@@ -319,19 +398,23 @@ __device__ __forceinline__ void publish(const EpiCtx& e) {
 __device__ __forceinline__ void stage_cs(const EpiCtx& e, int slot, int chunk, float d) {
   if ((e.lane & 1) == 0) e.cs_s[(slot * 8 + e.we) * 64 + chunk * 16 + (e.lane >> 1)] = d;
 }
-__device__ __forceinline__ float reduce_cs(const EpiCtx& e, int slot, int col) {  // col 0..127 of the tile
-  const int hf = col >> 6, cc = col & 63;
+// col: column of the tile; cw: columns per epilogue warp (64 for 128-wide tiles, 32 for the 64-wide loss tiles)
+__device__ __forceinline__ float reduce_cs(const EpiCtx& e, int slot, int col, int cw = 64) {
+  const int hf = col / cw, cc = col - hf * cw;
   float s = 0.f;
 #pragma unroll
   for (int quarter = 0; quarter < 4; ++quarter) s += e.cs_s[(slot * 8 + hf * 4 + ((quarter - 2) & 3)) * 64 + cc];
   return s;
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(bf16 a, bf16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// weights of both towers -> bf16 terms: (a) one flat float4 pass over all matrices for the row-major terms, every
+// load of a thread in flight at once; (b) 64 x 64 tiles through shared memory for the transposed copies
 __device__ void epi_split(const ChainParams& p, EpiCtx& e, int task_i) {
-  const int tx = e.tid & 31, ty = e.tid >> 5;  // 32 x 8
-  bf16(*s_hi)[33] = reinterpret_cast<bf16(*)[33]>(e.sp_s);
-  bf16(*s_lo)[33] = reinterpret_cast<bf16(*)[33]>(e.sp_s + 32 * 33);
-  const int stride = p.off[T_F1] - p.off[T_S];
+  const int nS = p.nS;
   if (task_i == 0 && e.tid == 0 && p.adam_state) {
     // torch.optim.Adam's step count and beta powers live on the device so that a graph replay advances them; the
     // tail (epi_grad) reads them through the S -> ... -> G dependency chain
@@ -340,54 +423,151 @@ __device__ void epi_split(const ChainParams& p, EpiCtx& e, int task_i) {
     p.adam_state[1] = (t == 0.0 ? 1.0 : p.adam_state[1]) * (double)p.beta1;
     p.adam_state[2] = (t == 0.0 ? 1.0 : p.adam_state[2]) * (double)p.beta2;
   }
-  for (int tile = task_i; tile < p.n_split_tiles; tile += stride) {
-    int ji = 0;
-    for (int k = 1; k < p.n_sj; ++k)
-      if (tile >= p.sj[k].tile0) ji = k;
-    const SplitJobC& J = p.sj[ji];
-    const int lt = tile - J.tile0;
-    const int r0 = (lt / J.tiles_c) * 32, c0 = (lt % J.tiles_c) * 32;
+  // (a) flat pass, first-layer weights first
+  constexpr int U = 4;
+  const int gstride = nS * kEpiThreads;
+  for (int part = 0; part < 2; ++part) {
+    const int lo_i = part ? p.n_split_f4_w1 : 0, hi_i = part ? p.n_split_f4 : p.n_split_f4_w1;
+    for (int base = lo_i + task_i * kEpiThreads + e.tid; base < hi_i; base += U * gstride) {
+      float4 v[U];
+      int ji[U], li[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * gstride;
+        ji[u] = -1;
+        if (i < hi_i) {
+          int j = 0;
+          for (int k = 1; k < p.n_sj; ++k)
+            if (i >= p.sj[k].f4_0) j = k;
+          ji[u] = j;
+          li[u] = i - p.sj[j].f4_0;
+          v[u] = __ldg(reinterpret_cast<const float4*>(p.sj[j].X) + li[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ji[u] < 0) continue;
+        const SplitJobC& J = p.sj[ji[u]];
+        const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        bf16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16(x[k], h[k], l[k]);
+        reinterpret_cast<uint2*>(J.hi)[li[u]] = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+        reinterpret_cast<uint2*>(J.lo)[li[u]] = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+        if (J.lo2) {
+          bf16 m[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            m[k] = __float2bfloat16_rn((x[k] - __bfloat162float(h[k])) - __bfloat162float(l[k]));
+          reinterpret_cast<uint2*>(J.lo2)[li[u]] = make_uint2(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]));
+        }
+      }
+    }
+    if (part == 0) {  // layer 1 can start
+      publish(e);
+      if (e.tid == 0) signal(p.ctr + 0);
+    }
+  }
+  // (b) transposed copies
+  bf16* s_hi = e.sp_s;
+  bf16* s_lo = e.sp_s + 64 * kSplitPad;
+  for (int tile = task_i; tile < p.n_split_t64; tile += nS) {
+    int j = -1;
+    for (int k = 0; k < p.n_sj; ++k)
+      if (p.sj[k].t64_0 >= 0 && tile >= p.sj[k].t64_0) j = k;
+    const SplitJobC& J = p.sj[j];
+    const int lt = tile - J.t64_0;
+    const int r0 = (lt / J.tiles_c) * 64, c0 = (lt % J.tiles_c) * 64;
+    float4 v[4];
+    const int rr = e.tid >> 4, c4 = e.tid & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[i] = __ldg(reinterpret_cast<const float4*>(J.X + (size_t)(r0 + rr + 16 * i) * J.C + c0) + c4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = r0 + ty + i * 8, c = c0 + tx;
-      bf16 h = __float2bfloat16_rn(0.f), l = h;
-      if (r < J.R && c < J.C) {
-        const float xv = J.X[(size_t)r * J.C + c];
-        split_bf16(xv, h, l);
-        if (J.hi) {
-          J.hi[(size_t)r * J.C + c] = h;
-          J.lo[(size_t)r * J.C + c] = l;
-        }
-        if (J.lo2) J.lo2[(size_t)r * J.C + c] = __float2bfloat16_rn((xv - __bfloat162float(h)) - __bfloat162float(l));
+      const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bf16 h, l;
+        split_bf16(x[k], h, l);
+        s_hi[(c4 * 4 + k) * kSplitPad + rr + 16 * i] = h;
+        s_lo[(c4 * 4 + k) * kSplitPad + rr + 16 * i] = l;
       }
-      s_hi[ty + i * 8][tx] = h;
-      s_lo[ty + i * 8][tx] = l;
     }
     epi_bar();
-    if (J.thi) {
+    // transposed tile: row c (64 of them) holds 64 consecutive r; a thread moves bf16 pairs, a warp one 128 B run
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + i * 8, r = r0 + tx;
-        if (r < J.R && c < J.C) {
-          J.thi[(size_t)c * J.ldt + r] = s_hi[tx][ty + i * 8];
-          J.tlo[(size_t)c * J.ldt + r] = s_lo[tx][ty + i * 8];
-        }
+    for (int i = 0; i < 8; ++i) {
+      const int item = e.tid + i * kEpiThreads;  // 64 rows x 32 pairs
+      const int cc = item >> 5, rp = item & 31;
+      const uint32_t a = *reinterpret_cast<const uint32_t*>(s_hi + cc * kSplitPad + 2 * rp);
+      const uint32_t b = *reinterpret_cast<const uint32_t*>(s_lo + cc * kSplitPad + 2 * rp);
+      const size_t o = (size_t)(c0 + cc) * J.R + r0 + 2 * rp;
+      *reinterpret_cast<uint32_t*>(J.thi + o) = a;
+      *reinterpret_cast<uint32_t*>(J.tlo + o) = b;
+    }
+    epi_bar();
+  }
+  publish(e);
+  if (e.tid == 0) signal(p.ctr + 2);
+}
+
+// xhat terms [3B, H] -> transposed [H, ldt] (query rows at columns [0, B), document rows from column dcol on): the
+// K-major operand of the first layer's weight gradient.  64 x 64 tiles through shared memory.
+__device__ void epi_transpose_x(const ChainParams& p, EpiCtx& e, int task_i) {
+  bf16* s_t[2] = {e.sp_s, e.sp_s + 64 * kSplitPad};
+  const bf16* src[2] = {p.x_hi, p.x_lo};
+  bf16* dst[2] = {p.xt_hi, p.xt_lo};
+  const int R = 3 * p.B, tiles_c = p.H / 64, ntiles = ((R + 63) / 64) * tiles_c;
+  for (int tile = task_i; tile < ntiles; tile += p.nS) {
+    const int r0 = (tile / tiles_c) * 64, c0 = (tile % tiles_c) * 64;
+    uint4 v[2][2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int item = e.tid + i * kEpiThreads, rr = item >> 3, sg = item & 7;  // 64 rows x 8 segments of 16 B
+        v[t][i] = (r0 + rr < R) ? __ldcg(reinterpret_cast<const uint4*>(src[t] + (size_t)(r0 + rr) * p.H + c0) + sg)
+                                : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int item = e.tid + i * kEpiThreads, rr = item >> 3, sg = item & 7;
+        const bf16* x = reinterpret_cast<const bf16*>(&v[t][i]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_t[t][(sg * 8 + k) * kSplitPad + rr] = x[k];
+      }
+    epi_bar();
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int item = e.tid + i * kEpiThreads;  // 64 transposed rows x 64 elements
+      const int cc = item >> 6, rr = item & 63, g = r0 + rr;
+      if (g < R) {
+        const size_t o = (size_t)(c0 + cc) * p.ldt + (g < p.B ? g : p.dcol + (g - p.B));
+        dst[0][o] = s_t[0][cc * kSplitPad + rr];
+        dst[1][o] = s_t[1][cc * kSplitPad + rr];
       }
     }
     epi_bar();
   }
   publish(e);
-  if (e.tid == 0) signal(p.ctr + 0);
+  if (e.tid == 0) signal(p.ctr + 3);
 }
+
+__device__ __forceinline__ int warp_valid_rows(const EpiCtx& e, int valid) { return max(0, min(32, valid - e.q * 32)); }
 
 __device__ void epi_f1(const ChainParams& p, EpiCtx& e, int task_i) {
   const RowTile rt = row_tile(p, task_i / p.NC);
   const int n0 = (task_i % p.NC) * BN;
   mbar_wait(&e.acc_full[e.ab], e.aph);
   tc_fence_after();
+  trace_ev(e, 2);
   const int row = e.q * 32 + e.lane;
   const bool ok = row < rt.valid;
-  const size_t grow = (size_t)rt.grow + row;
+  const int vr = warp_valid_rows(e, rt.valid);
+  const size_t wrow0 = (size_t)rt.grow + e.q * 32;
   const int tcol = (rt.t ? p.dcol : 0) + rt.trow + row;
   const float* bias = p.b1[rt.t];
   for (int ch = 0; ch < 4; ++ch) {
@@ -397,10 +577,18 @@ __device__ void epi_f1(const ChainParams& p, EpiCtx& e, int task_i) {
     tmem_ld16(acc_addr(e, e.ab, ch), v);
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(bias + n + j), 0.f);
-    if (!ok) continue;
-    const size_t o = grow * p.P + n;
-    store16(p.h + o, v);
-    store_terms(v, p.h_hi, p.h_lo, o, p.ht_hi, p.ht_lo, n, p.ldt, tcol);
+    alignas(16) bf16 hi[16], lo[16];
+    split16(v, hi, lo);
+    stage16(e.rs, e.lane, hi);
+    stage16(e.rs + kTermBlock, e.lane, lo);
+    if (ok) {
+      store_t(hi, lo, p.ht_hi, p.ht_lo, n, p.ldt, tcol);
+      if (p.h) store16(p.h + (wrow0 + e.lane) * p.P + n, v);
+    }
+    __syncwarp();
+    flush16(e.rs, e.lane, p.h_hi, wrow0, n, p.P, vr);
+    flush16(e.rs + kTermBlock, e.lane, p.h_lo, wrow0, n, p.P, vr);
+    __syncwarp();
   }
   tc_fence_before();
   mbar_arrive(&e.acc_empty[e.ab]);
@@ -409,59 +597,90 @@ __device__ void epi_f1(const ChainParams& p, EpiCtx& e, int task_i) {
   if (e.tid == 0) signal(h_ready(p) + rt.seg * p.RTB + rt.r);
 }
 
+// Layer 2 and the loss.  Task ((r, c), seg) owns the 128 x 64 tile of y for ONE row group (q | p | n) of 128 triplets:
+//   1. y = acc + b2 goes to an exchange buffer (layout [column][row]: every access of a warp is one 128 B line) and
+//      the accumulator is released; the three tasks of (r, c) run on three CTAs at the same time and wait for each other;
+//   2. every task reads all three tiles and forms the partial |q|^2, |p|^2, |n|^2, q.p, q.n of its columns; the seg 0
+//      task publishes them; all tasks of row tile r wait until the partials of every column tile have arrived;
+//   3. cosines, hinge, and the closed-form dY of the task's OWN row group -> (hi, lo) terms row-major and transposed,
+//      db2 partial sums.
 __device__ void epi_f2l(const ChainParams& p, EpiCtx& e, int task_i) {
-  const int r = task_i / p.NC, c = task_i % p.NC, n0 = c * BN;
+  const int seg = task_i % 3, rc = task_i / 3, r = rc / p.NCF, c = rc % p.NCF, n0 = c * 64;
   const int valid = min(BM, p.B - r * BM);
   const int row = e.q * 32 + e.lane;
   const bool ok = row < valid;
+  const int vr = warp_valid_rows(e, valid);
   const int trip = r * BM + row;
-  int buf[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int idx = e.ab + k;
-    buf[k] = idx & (kAcc - 1);
-    mbar_wait(&e.acc_full[buf[k]], e.aph ^ (uint32_t)(idx >> 2));
-  }
+  const size_t wrow0 = (size_t)seg * p.B + (size_t)r * BM + e.q * 32;  // this warp's first row in the [3B, P] arrays
+  mbar_wait(&e.acc_full[e.ab], e.aph);
   tc_fence_after();
-  const float *bq = p.b2[0], *bd = p.b2[1];
-  // ---- pass 1: y, partial dot products over this thread's 64 columns ---------------------------------------
-  float qq = 0.f, pp = 0.f, nn = 0.f, qp = 0.f, qn = 0.f;
-  for (int ch = 0; ch < 4; ++ch) {
-    const int n = n0 + e.hf * 64 + ch * 16;
-    if (n >= p.P) break;
-    float vq[16], vp[16], vn[16];
-    tmem_ld16(acc_addr(e, buf[0], ch), vq);
-    tmem_ld16(acc_addr(e, buf[1], ch), vp);
-    tmem_ld16(acc_addr(e, buf[2], ch), vn);
+  trace_ev(e, 2);
+  const uint32_t accb = e.tmem_base + ((uint32_t)(e.q * 32) << 16) + (uint32_t)(e.ab * BN + e.hf * 32);
+  const float* bias = p.b2[seg != 0];
+  float* X = p.ybuf + (size_t)rc * 3 * 64 * 128;  // [seg][64 columns][128 rows]
+  float own[32];  // this task's y values of the thread's 32 columns stay in registers
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const int col = e.hf * 32 + ch * 16;
+    float v[16];
+    tmem_ld16(accb + ch * 16, v);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float a = vq[j] + __ldg(bq + n + j), b = vp[j] + __ldg(bd + n + j), d = vn[j] + __ldg(bd + n + j);
-      vq[j] = a; vp[j] = b; vn[j] = d;
-      qq = fmaf(a, a, qq);
-      pp = fmaf(b, b, pp);
-      nn = fmaf(d, d, nn);
-      qp = fmaf(a, b, qp);
-      qn = fmaf(a, d, qn);
+      v[j] += __ldg(bias + n0 + col + j);
+      own[ch * 16 + j] = v[j];
+      X[((size_t)(seg * 64 + col + j)) * 128 + row] = v[j];
     }
-    if (p.y && ok) {
-      store16(p.y + (size_t)trip * p.P + n, vq);
-      store16(p.y + (size_t)(p.B + trip) * p.P + n, vp);
-      store16(p.y + (size_t)(2 * p.B + trip) * p.P + n, vn);
-    }
+    if (p.y && ok) store16(p.y + ((size_t)seg * p.B + trip) * p.P + n0 + col, v);
   }
-  const int nslots = 2 * p.NC;
-  {
-    float* sp = p.stat_part + ((size_t)(r * nslots + c * 2 + e.hf) * 5) * 128 + row;
-    sp[0] = qq; sp[128] = pp; sp[256] = nn; sp[384] = qp; sp[512] = qn;
-  }
+  tc_fence_before();
+  mbar_arrive(&e.acc_empty[e.ab]);  // the accumulator is free: the next main loop may overwrite it
+  acc_advance(e, 1);
   __threadfence();
   epi_bar();
   if (e.tid == 0) {
-    signal(stat_ready(p) + r);
-    wait_counter(stat_ready(p) + r, (unsigned)p.NC);
+    signal(y_ready(p) + rc);
+    wait_counter(y_ready(p) + rc, 3u);
   }
   epi_bar();
-  // ---- the whole row's sums, slot order fixed (identical in every sibling tile) ------------------------------
+  // ---- the other two row groups' values of the same (triplet, column)s: all 64 loads in flight at once -----------------
+  const int s1 = seg == 0 ? 1 : 0, s2 = seg == 2 ? 1 : 2;  // the two foreign groups, ascending
+  float f1[32], f2[32];
+  {
+    const float* x1 = X + (size_t)(s1 * 64 + e.hf * 32) * 128 + row;
+    const float* x2 = X + (size_t)(s2 * 64 + e.hf * 32) * 128 + row;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      f1[j] = __ldcg(x1 + (size_t)j * 128);
+      f2[j] = __ldcg(x2 + (size_t)j * 128);
+    }
+  }
+  // q, p, n views of (own, f1, f2): seg 0 -> (own, f1, f2), seg 1 -> (f1, own, f2), seg 2 -> (f1, f2, own)
+  float qq = 0.f, pp = 0.f, nn = 0.f, qp = 0.f, qn = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float a = seg == 0 ? own[j] : f1[j];
+    const float b = seg == 0 ? f1[j] : (seg == 1 ? own[j] : f2[j]);
+    const float d = seg == 2 ? own[j] : f2[j];
+    qq = fmaf(a, a, qq);
+    pp = fmaf(b, b, pp);
+    nn = fmaf(d, d, nn);
+    qp = fmaf(a, b, qp);
+    qn = fmaf(a, d, qn);
+  }
+  const int nslots = 2 * p.NCF;
+  if (seg == 0) {
+    float* sp = p.stat_part + ((size_t)(r * nslots + c * 2 + e.hf) * 5) * 128 + row;
+    sp[0] = qq; sp[128] = pp; sp[256] = nn; sp[384] = qp; sp[512] = qn;
+    __threadfence();
+  }
+  epi_bar();
+  if (e.tid == 0) {
+    if (seg == 0) signal(stat_ready(p) + r);
+    wait_counter(stat_ready(p) + r, (unsigned)p.NCF);
+  }
+  epi_bar();
+  trace_ev(e, 3);
+  // ---- the whole row's sums, slot order fixed (identical in every task of this row tile) ------------------------
   qq = pp = nn = qp = qn = 0.f;
   for (int s = 0; s < nslots; ++s) {
     const float* sp = p.stat_part + ((size_t)(r * nslots + s) * 5) * 128 + row;
@@ -472,12 +691,18 @@ __device__ void epi_f2l(const ChainParams& p, EpiCtx& e, int task_i) {
   const float cos_p = qp / (cq * cp), cos_n = qn / (cq * cn);
   // relu(pos_dist - neg_dist + margin), model.py:140-143
   const float hinge = ok ? fmaxf((1.f - cos_p) - (1.f - cos_n) + p.margin, 0.f) : 0.f;
-  const float gh = (hinge > 0.f) ? p.grad_scale * p.inv_batch : 0.f;
+  const float gh = (hinge > 0.f) ? p.grad_scale * p.inv_batch : 0.f;  // 0 for rows past the batch: their dY is 0
+  // dY of this task's row group = c_own * own + c1 * f1 + c2 * f2  (closed-form gradient of the two cosines)
   const float a_qp = -gh / (cq * cp), a_qn = gh / (cq * cn);
-  const float kq = (nq > kCosEps) ? (-gh * cos_p + gh * cos_n) / (cq * nq) : 0.f;
-  const float kp = (np_ > kCosEps) ? (-gh * cos_p) / (cp * np_) : 0.f;
-  const float kn = (nn_ > kCosEps) ? (gh * cos_n) / (cn * nn_) : 0.f;
-  if (c == 0 && e.hf == 0) {
+  float c_own, c1, c2;
+  if (seg == 0) {  // dq = a_qp p + a_qn n - kq q
+    c_own = -((nq > kCosEps) ? (-gh * cos_p + gh * cos_n) / (cq * nq) : 0.f); c1 = a_qp; c2 = a_qn;
+  } else if (seg == 1) {  // dp = a_qp q - kp p
+    c_own = -((np_ > kCosEps) ? (-gh * cos_p) / (cp * np_) : 0.f); c1 = a_qp; c2 = 0.f;
+  } else {  // dn = a_qn q - kn n
+    c_own = -((nn_ > kCosEps) ? (gh * cos_n) / (cn * nn_) : 0.f); c1 = a_qn; c2 = 0.f;
+  }
+  if (seg == 0 && c == 0 && e.hf == 0) {
     if (ok) {
       float* s = p.stats + (size_t)trip * 8;
       s[0] = cos_p; s[1] = cos_n; s[2] = hinge; s[3] = nq; s[4] = np_; s[5] = nn_; s[6] = qp; s[7] = qn;
@@ -485,52 +710,36 @@ __device__ void epi_f2l(const ChainParams& p, EpiCtx& e, int task_i) {
     const float hsum = warp_sum(hinge);
     if (e.lane == 0) e.hs_s[e.q] = hsum;
   }
-  // ---- pass 2: dY from the accumulators still in TMEM ---------------------------------------------------------
-  for (int ch = 0; ch < 4; ++ch) {
-    const int n = n0 + e.hf * 64 + ch * 16;
-    if (n >= p.P) break;
-    float vq[16], vp[16], vn[16];
-    tmem_ld16(acc_addr(e, buf[0], ch), vq);
-    tmem_ld16(acc_addr(e, buf[1], ch), vp);
-    tmem_ld16(acc_addr(e, buf[2], ch), vn);
-    float gq[16], gp[16], gn[16];
+  const int tcol = seg == 0 ? trip : p.dcol + (seg - 1) * p.B + trip;
+  uint8_t* blk_hi = e.rs;
+  uint8_t* blk_lo = e.rs + kTermBlock;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float a = vq[j] + __ldg(bq + n + j), b = vp[j] + __ldg(bd + n + j), d = vn[j] + __ldg(bd + n + j);
-      gq[j] = ok ? (a_qp * b + a_qn * d - kq * a) : 0.f;
-      gp[j] = ok ? (a_qp * a - kp * b) : 0.f;
-      gn[j] = ok ? (a_qn * a - kn * d) : 0.f;
-    }
+  for (int ch = 0; ch < 2; ++ch) {
+    const int n = n0 + e.hf * 32 + ch * 16;
+    float g[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      g[j] = ok ? (c_own * own[ch * 16 + j] + c1 * f1[ch * 16 + j] + c2 * f2[ch * 16 + j]) : 0.f;
+    alignas(16) bf16 hi[16], lo[16];
+    split16(g, hi, lo);
+    stage16(blk_hi, e.lane, hi);
+    stage16(blk_lo, e.lane, lo);
     if (ok) {
-      const size_t oq = (size_t)trip * p.P + n, op = (size_t)(p.B + trip) * p.P + n,
-                   on = (size_t)(2 * p.B + trip) * p.P + n;
-      if (p.dy) {
-        store16(p.dy + oq, gq);
-        store16(p.dy + op, gp);
-        store16(p.dy + on, gn);
-      }
-      store_terms(gq, p.dy_hi, p.dy_lo, oq, p.dyt_hi, p.dyt_lo, n, p.ldt, trip);
-      store_terms(gp, p.dy_hi, p.dy_lo, op, p.dyt_hi, p.dyt_lo, n, p.ldt, p.dcol + trip);
-      store_terms(gn, p.dy_hi, p.dy_lo, on, p.dyt_hi, p.dyt_lo, n, p.ldt, p.dcol + p.B + trip);
+      store_t(hi, lo, p.dyt_hi, p.dyt_lo, n, p.ldt, tcol);
+      if (p.dy) store16(p.dy + ((size_t)seg * p.B + trip) * p.P + n, g);
     }
-    stage_cs(e, 0, ch, colsum16(gq, e.lane));
-#pragma unroll
-    for (int j = 0; j < 16; ++j) gp[j] += gn[j];
-    stage_cs(e, 1, ch, colsum16(gp, e.lane));
+    __syncwarp();
+    flush16(blk_hi, e.lane, p.dy_hi, wrow0, n, p.P, vr);
+    flush16(blk_lo, e.lane, p.dy_lo, wrow0, n, p.P, vr);
+    __syncwarp();
+    stage_cs(e, 0, ch, colsum16(g, e.lane));
   }
-  tc_fence_before();
-#pragma unroll
-  for (int k = 0; k < 3; ++k) mbar_arrive(&e.acc_empty[buf[k]]);
-  acc_advance(e, 3);
   epi_bar();
-  if (e.tid < BN && n0 + e.tid < p.P) {  // db2 partials of this triplet tile: query tower | document tower (p + n)
-    p.cs2[(size_t)r * p.P + n0 + e.tid] = reduce_cs(e, 0, e.tid);
-    p.cs2[(size_t)(p.RTB + r) * p.P + n0 + e.tid] = reduce_cs(e, 1, e.tid);
-  }
-  if (c == 0 && e.tid == 0) p.hinge_part[r] = (e.hs_s[0] + e.hs_s[1]) + (e.hs_s[2] + e.hs_s[3]);
+  if (e.tid < 64) p.cs2[(size_t)(seg * p.RTB + r) * p.P + n0 + e.tid] = reduce_cs(e, 0, e.tid, 32);  // db2 partials
+  if (seg == 0 && c == 0 && e.tid == 0) p.hinge_part[r] = (e.hs_s[0] + e.hs_s[1]) + (e.hs_s[2] + e.hs_s[3]);
   publish(e);
   if (e.tid == 0) {
-    for (int seg = 0; seg < 3; ++seg) signal(dy_ready(p) + seg * p.RTB + r);
+    signal(dy_ready(p) + seg * p.RTB + r);
     signal(p.ctr + 1);
   }
 }
@@ -540,31 +749,40 @@ __device__ void epi_dz(const ChainParams& p, EpiCtx& e, int task_i) {
   const int n0 = (task_i % p.NC) * BN;
   mbar_wait(&e.acc_full[e.ab], e.aph);
   tc_fence_after();
+  trace_ev(e, 2);
   const int row = e.q * 32 + e.lane;
   const bool ok = row < rt.valid;
-  const size_t grow = (size_t)rt.grow + row;
+  const int vr = warp_valid_rows(e, rt.valid);
+  const size_t wrow0 = (size_t)rt.grow + e.q * 32;
   const int tcol = (rt.t ? p.dcol : 0) + rt.trow + row;
   for (int ch = 0; ch < 4; ++ch) {
     const int n = n0 + e.hf * 64 + ch * 16;
     if (n >= p.P) break;
     float v[16];
     tmem_ld16(acc_addr(e, e.ab, ch), v);
-    const size_t o = grow * p.P + n;
+    const size_t o = (wrow0 + e.lane) * p.P + n;
     if (ok) {
-      const float4* gp = reinterpret_cast<const float4*>(p.h + o);
+      // ReLU gate from the hi term of h: bf16 rounding keeps the sign and never turns a normal positive value into 0
+      alignas(16) bf16 g[16];
+      reinterpret_cast<uint4*>(g)[0] = __ldcg(reinterpret_cast<const uint4*>(p.h_hi + o));
+      reinterpret_cast<uint4*>(g)[1] = __ldcg(reinterpret_cast<const uint4*>(p.h_hi + o) + 1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 t = __ldcg(gp + j);
-        v[4 * j + 0] = t.x > 0.f ? v[4 * j + 0] : 0.f;
-        v[4 * j + 1] = t.y > 0.f ? v[4 * j + 1] : 0.f;
-        v[4 * j + 2] = t.z > 0.f ? v[4 * j + 2] : 0.f;
-        v[4 * j + 3] = t.w > 0.f ? v[4 * j + 3] : 0.f;
-      }
+      for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(g[j]) > 0.f ? v[j] : 0.f;
       if (p.dz1) store16(p.dz1 + o, v);
-      store_terms(v, p.dz_hi, p.dz_lo, o, p.dzt_hi, p.dzt_lo, n, p.ldt, tcol);
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+    alignas(16) bf16 hi[16], lo[16];
+    split16(v, hi, lo);
+    if (ok) store_t(hi, lo, p.dzt_hi, p.dzt_lo, n, p.ldt, tcol);
+    if (p.dz_hi) {
+      stage16(e.rs, e.lane, hi);
+      stage16(e.rs + kTermBlock, e.lane, lo);
+      __syncwarp();
+      flush16(e.rs, e.lane, p.dz_hi, wrow0, n, p.P, vr);
+      flush16(e.rs + kTermBlock, e.lane, p.dz_lo, wrow0, n, p.P, vr);
+      __syncwarp();
     }
     stage_cs(e, 0, ch, colsum16(v, e.lane));
   }
@@ -581,20 +799,28 @@ __device__ void epi_dz(const ChainParams& p, EpiCtx& e, int task_i) {
   }
 }
 
+// fp32 tile of this warp (32 rows x 64 columns) -> g, through the staging block, 16 columns at a time
+__device__ __forceinline__ void epi_store_f32(const ChainParams& p, EpiCtx& e, float* g, size_t wrow0, int n0, int N,
+                                              size_t ld, int vr) {
+  for (int ch = 0; ch < 4; ++ch) {
+    const int n = n0 + e.hf * 64 + ch * 16;
+    if (n >= N) break;
+    float v[16];
+    tmem_ld16(acc_addr(e, e.ab, ch), v);
+    stage_f32(e.rs, e.lane, v);
+    __syncwarp();
+    flush_f32(e.rs, e.lane, g, wrow0, n, ld, vr);
+    __syncwarp();
+  }
+}
+
 __device__ void epi_dx(const ChainParams& p, EpiCtx& e, int task_i) {
   const RowTile rt = row_tile(p, task_i / p.NCH);
   const int n0 = (task_i % p.NCH) * BN;
   mbar_wait(&e.acc_full[e.ab], e.aph);
   tc_fence_after();
-  const int row = e.q * 32 + e.lane;
-  const bool ok = row < rt.valid;
-  for (int ch = 0; ch < 4; ++ch) {
-    const int n = n0 + e.hf * 64 + ch * 16;
-    if (n >= p.H) break;
-    float v[16];
-    tmem_ld16(acc_addr(e, e.ab, ch), v);
-    if (ok) store16(p.dxhat + ((size_t)rt.grow + row) * p.H + n, v);
-  }
+  trace_ev(e, 2);
+  epi_store_f32(p, e, p.dxhat, (size_t)rt.grow + e.q * 32, n0, p.H, p.H, warp_valid_rows(e, rt.valid));
   tc_fence_before();
   mbar_arrive(&e.acc_empty[e.ab]);
   acc_advance(e, 1);
@@ -605,17 +831,12 @@ __device__ void epi_dw(const ChainParams& p, EpiCtx& e, Task tk) {
   const bool two = tk.type == T_DW2;
   const int N = two ? p.P : p.H, ntn = two ? p.NC : p.NCH, nt_ = p.NC * ntn;
   const int ci = tk.i / nt_, tile = tk.i % nt_;
-  const int m = (tile / ntn) * BM + e.q * 32 + e.lane, n0 = (tile % ntn) * BN;
+  const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
   float* part = (two ? p.part2 : p.part1) + (size_t)ci * p.P * N;
   mbar_wait(&e.acc_full[e.ab], e.aph);
   tc_fence_after();
-  for (int ch = 0; ch < 4; ++ch) {
-    const int n = n0 + e.hf * 64 + ch * 16;
-    if (n >= N) break;
-    float v[16];
-    tmem_ld16(acc_addr(e, e.ab, ch), v);
-    if (m < p.P) store16(part + (size_t)m * N + n, v);
-  }
+  trace_ev(e, 2);
+  epi_store_f32(p, e, part, (size_t)m0 + e.q * 32, n0, N, N, warp_valid_rows(e, p.P - m0));
   tc_fence_before();
   mbar_arrive(&e.acc_empty[e.ab]);
   acc_advance(e, 1);
@@ -668,6 +889,7 @@ __device__ __forceinline__ void emit1(const ChainParams& p, const AdamCoef& k, f
 __device__ void epi_grad(const ChainParams& p, EpiCtx& e, int task_i) {
   if (e.tid == 0) wait_counter(p.ctr + 1, p.total_signals);
   epi_bar();
+  trace_ev(e, 2);
   AdamCoef k{0.f, 1.f};
   if (p.adam_p) {
     const volatile double* st = p.adam_state;
@@ -676,44 +898,86 @@ __device__ void epi_grad(const ChainParams& p, EpiCtx& e, int task_i) {
   }
   const int nG = p.off[T_COUNT] - p.off[T_G];
   const size_t gid = (size_t)task_i * kEpiThreads + e.tid, gstride = (size_t)nG * kEpiThreads;
-  for (int t = 0; t < 2; ++t) {
+  // the four weight gradients as one list of float4 items; a thread keeps two items and, per item, four chunk loads
+  // in flight (the additions keep chunk order)
+  const size_t n2 = (size_t)p.P * p.P / 4, n1 = (size_t)p.P * p.H / 4, ntot = 2 * (n2 + n1);
+  auto locate = [&](size_t item, const float4*& src, float4*& dst, size_t& n4, int& nch) {
+    const int t = item >= n2 + n1;
+    size_t i = item - (t ? n2 + n1 : 0);
     const int c0 = t ? p.nch[0] : 0;
-    {
-      const size_t n4 = (size_t)p.P * p.P / 4;
-      const float4* src = reinterpret_cast<const float4*>(p.part2) + (size_t)c0 * n4;
-      float4* dst = reinterpret_cast<float4*>(p.dW2[t]);
-      for (size_t i = gid; i < n4; i += gstride) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < p.nch[t]; ++j) acc = add4(acc, __ldcg(src + (size_t)j * n4 + i));
-        emit4(p, k, dst + i, acc);
-      }
+    nch = p.nch[t];
+    if (i < n2) {
+      n4 = n2;
+      src = reinterpret_cast<const float4*>(p.part2) + (size_t)c0 * n2 + i;
+      dst = reinterpret_cast<float4*>(p.dW2[t]) + i;
+    } else {
+      i -= n2;
+      n4 = n1;
+      src = reinterpret_cast<const float4*>(p.part1) + (size_t)c0 * n1 + i;
+      dst = reinterpret_cast<float4*>(p.dW1[t]) + i;
     }
-    {
-      const size_t n4 = (size_t)p.P * p.H / 4;
-      const float4* src = reinterpret_cast<const float4*>(p.part1) + (size_t)c0 * n4;
-      float4* dst = reinterpret_cast<float4*>(p.dW1[t]);
-      for (size_t i = gid; i < n4; i += gstride) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < p.nch[t]; ++j) acc = add4(acc, __ldcg(src + (size_t)j * n4 + i));
-        emit4(p, k, dst + i, acc);
-      }
+  };
+  for (size_t it = gid; it < ntot; it += 2 * gstride) {
+    const float4* src[2];
+    float4* dst[2];
+    size_t n4[2];
+    int nch[2];
+    const bool two = it + gstride < ntot;
+    locate(it, src[0], dst[0], n4[0], nch[0]);
+    locate(two ? it + gstride : it, src[1], dst[1], n4[1], nch[1]);
+    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    const int nmax = max(nch[0], nch[1]);
+    for (int j = 0; j < nmax; j += 4) {
+      float4 t[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          t[u][k] = (j + k < nch[u]) ? __ldcg(src[u] + (size_t)(j + k) * n4[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (j + k < nch[u]) acc[u] = add4(acc[u], t[u][k]);
     }
-    for (size_t n = gid; n < (size_t)p.P; n += gstride) {
-      float s2 = 0.f, s1 = 0.f;
-      for (int r = 0; r < p.RTB; ++r) s2 += __ldcg(p.cs2 + (size_t)(t * p.RTB + r) * p.P + n);
-      if (t == 0) {
-        for (int r = 0; r < p.RTB; ++r) s1 += __ldcg(p.cs1 + (size_t)r * p.P + n);
+    emit4(p, k, dst[0], acc[0]);
+    if (two) emit4(p, k, dst[1], acc[1]);
+  }
+  // bias gradients: one output per warp at a time, the lanes take the row-tile partials (lane-strided, then a fixed
+  // xor tree), so every CTA shares this tail instead of the first few
+  {
+    const int nout = 4 * p.P;  // db2[0] | db2[1] | db1[0] | db1[1]
+    const int gw = task_i * 8 + e.we, nw = nG * 8;
+    for (int o = gw; o < nout; o += nw) {
+      const int which = o / p.P, n = o - which * p.P, t = which & 1;
+      const float* src;
+      int cnt;
+      if (which < 2) {
+        src = p.cs2 + (size_t)(t ? p.RTB : 0) * p.P + n;
+        cnt = t ? 2 * p.RTB : p.RTB;
       } else {
-        for (int r = 0; r < 2 * p.RTB; ++r) s1 += __ldcg(p.cs1 + (size_t)(p.RTB + r) * p.P + n);
+        src = p.cs1 + (size_t)(t ? p.RTB : 0) * p.P + n;
+        cnt = t ? 2 * p.RTB : p.RTB;
       }
-      emit1(p, k, p.db2[t] + n, s2);
-      emit1(p, k, p.db1[t] + n, s1);
+      float s = 0.f;
+      for (int r = e.lane; r < cnt; r += 32) s += __ldcg(src + (size_t)r * p.P);
+      s = warp_sum(s);
+      if (e.lane == 0) emit1(p, k, (which < 2 ? p.db2[t] : p.db1[t]) + n, s);
     }
   }
   if (task_i == 0 && e.tid == 0) {
     float s = 0.f;
     for (int r = 0; r < p.RTB; ++r) s += __ldcg(p.hinge_part + r);
     *p.loss = s * p.inv_batch;
+  }
+  // The last tail task to finish clears the dependency counters for the next launch (every other task of this
+  // launch has completed by then: the tail waited for all of them), so a graph replay needs no memset node.
+  epi_bar();
+  if (e.tid == 0) {
+    __threadfence();
+    if (atomicAdd(p.ctr + 4, 1u) == (unsigned)nG - 1u) {
+      for (int i = 0; i < p.n_counters; ++i) p.ctr[i] = 0u;
+    }
   }
 }
 
@@ -755,6 +1019,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     if (elect_one()) {  // ---- TMA producer: dependencies, then the operand tiles of every sub-tile ------------
       int s = 0;
       uint32_t ph = 0;
+      if (p.use_pdl) pdl_wait();
       for (int idx = blockIdx.x; idx < n_tasks; idx += gridDim.x) {
         const Task tk = decode(p, idx);
         const int ns = n_subs(tk.type);
@@ -763,12 +1028,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         fence_proxy_async();  // other CTAs' generic-proxy writes (acquired above) before this thread's TMA reads
         for (int k = 0; k < ns; ++k) {
           const Sub sb = get_sub(p, tk, k);
-          for (int kbi = 0; kbi < sb.nkb; ++kbi) {
+          // CTAs working on the same operand (every row tile reads the same weight tiles) start at different k-blocks,
+          // so that they do not all pull the same L2 lines at the same moment; the order is fixed per task
+          int kb = sb.kb0 + (p.krot ? (int)(blockIdx.x % (unsigned)sb.nkb) : 0);
+          for (int kbi = 0; kbi < sb.nkb; ++kbi, kb = (kb + 1 == sb.kb0 + sb.nkb) ? sb.kb0 : kb + 1) {
             for (int j = 0; j < sb.terms; ++j) {
               mbar_wait(&empty[s], ph ^ 1u);
-              mbar_arrive_expect_tx(&full[s], kStageBytes);
-              tma_load_2d(smem + s * kStageBytes, &sb.a[j], &full[s], (sb.kb0 + kbi) * BK, sb.m0);
-              tma_load_2d(smem + s * kStageBytes + kABytes, &sb.b[j], &full[s], (sb.kb0 + kbi) * BK, sb.n0);
+              mbar_arrive_expect_tx(&full[s], kABytes + (uint32_t)sb.bn * BK * 2);
+              tma_load_2d(smem + s * kStageBytes, &sb.a[j], &full[s], kb * BK, sb.m0);
+              tma_load_2d(smem + s * kStageBytes + kABytes, &sb.b[j], &full[s], kb * BK, sb.n0);
               if (++s == NS) {
                 s = 0;
                 ph ^= 1u;
@@ -780,7 +1048,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {  // ---- MMA issuer ----------------------------------------------------------------------
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc128 = make_idesc_bf16(BM, BN), idesc64 = make_idesc_bf16(BM, 64);
       const uint32_t ring = smem_u32(smem);
       int s = 0, ab = 0;
       uint32_t ph = 0, aph = 0;
@@ -789,6 +1057,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         const int ns = n_subs(tk.type);
         for (int k = 0; k < ns; ++k) {
           const Sub sb = get_sub(p, tk, k);
+          const uint32_t idesc = sb.bn == BN ? idesc128 : idesc64;
           mbar_wait(&acc_empty[ab], aph ^ 1u);
           tc_fence_after();
           const uint32_t acc = tmem_base + (uint32_t)(ab * BN);
@@ -829,8 +1098,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     e.acc_full = acc_full;
     e.acc_empty = acc_empty;
     e.cs_s = reinterpret_cast<float*>(staging);
-    e.sp_s = reinterpret_cast<bf16*>(staging + 2 * 8 * 64 * 4);
-    e.hs_s = reinterpret_cast<float*>(staging + 2 * 8 * 64 * 4 + 2 * 32 * 33 * 2);
+    e.sp_s = reinterpret_cast<bf16*>(staging + kCsBytes);
+    e.rs = staging + kCsBytes + (warp - 2) * kRowStage;
+    e.hs_s = reinterpret_cast<float*>(staging + kCsBytes + 8 * kRowStage);
     e.we = warp - 2;
     e.q = warp & 3;
     e.hf = e.we >> 2;
@@ -838,10 +1108,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     e.tid = threadIdx.x - 64;
     e.ab = 0;
     e.aph = 0;
+    e.trace = p.trace ? p.trace + (size_t)blockIdx.x * kTraceSlots * 2 : nullptr;
+    e.tslot = 0;
     for (int idx = blockIdx.x; idx < n_tasks; idx += gridDim.x) {
       const Task tk = decode(p, idx);
+      e.tidx = idx;
+      trace_ev(e, 0);
       switch (tk.type) {
-        case T_S: epi_split(p, e, tk.i); break;
+        case T_S:
+          epi_split(p, e, tk.i);
+          if (p.use_pdl) pdl_wait();  // the pooled gather's xhat terms are read from here on
+          break;
+        case T_T: epi_transpose_x(p, e, tk.i); break;
         case T_F1: epi_f1(p, e, tk.i); break;
         case T_F2L: epi_f2l(p, e, tk.i); break;
         case T_DZ: epi_dz(p, e, tk.i); break;
@@ -850,6 +1128,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         case T_DW1: epi_dw(p, e, tk); break;
         default: epi_grad(p, e, tk.i); break;
       }
+      trace_ev(e, 1);
     }
   }
   tc_fence_before();
@@ -862,24 +1141,21 @@ int chain_stages() {
   if (v < 0) {
     const char* e = getenv("TT_CHAIN_STAGES");
     v = e ? atoi(e) : 0;
-    if (v < 3 || v > kMaxStages) v = 5;
+    if (v < 3 || v > kMaxStages) v = 5;  // (6 x 32 KB + 29 KB of epilogue staging still fit the 227 KB; 5 measured best)
   }
   return v;
 }
 
-int chain_debug_out() {  // TT_CHAIN_FP32_OUT=1: also write y, dY and dz1 in fp32 (diagnostics)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TT_CHAIN_FP32_OUT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+int chain_debug_out() {  // TT_CHAIN_FP32_OUT=1: also write h, y, dY and dz1 in fp32 (diagnostics; read per call)
+  const char* e = getenv("TT_CHAIN_FP32_OUT");
+  return e ? atoi(e) : 0;
 }
 
-int map_terms(CUtensorMap* m, int n, const bf16* const* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+int map_terms(CUtensorMap* m, int n, const bf16* const* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+              uint32_t box_rows = BM) {
   for (int i = 0; i < n; ++i) {
     const bf16* base = ptr[i] ? ptr[i] : ptr[0];  // unused terms alias the first (never loaded)
-    int rc = make_map_bf16_kmajor(&m[i], base, rows, cols, ld, BM);
+    int rc = make_map_bf16_kmajor(&m[i], base, rows, cols, ld, box_rows);
     if (rc) return rc;
   }
   return 0;
@@ -892,15 +1168,17 @@ bool chain_enabled() {
   return e ? atoi(e) != 0 : true;
 }
 
-// Everything of the step after the pooled gather.  s.adam (optional): torch.optim.Adam on the flat parameter buffer in
+// Everything of the step after the pooled gather.  after_gather: the pooled gather is the previous launch of this
+// stream (whole-step call): the kernel is then launched as its programmatic dependent, splits the weights while the
+// gather's last CTAs drain and waits for it (griddepcontrol.wait) before it reads xhat.  s.adam (optional): torch.optim.Adam on the flat parameter buffer in
 // the kernel's tail, step count and beta powers advanced on the device.
-int chain_sm100(const StepSm100& s, cudaStream_t st) {
+int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st) {
   const int B = s.B, H = s.H, P = s.P;
   StepWs w;
   carve_step(reinterpret_cast<char*>(s.ws), B, H, P, s.dxhat != nullptr, &w);
   static bool attr_done = false;
   if (!attr_done) {
-    TT_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(kMaxStages)));
+    TT_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem(chain_stages())));
     attr_done = true;
   }
   static thread_local ChainParams p;  // ~8 KB: kept off the stack; copied into the launch before this returns
@@ -928,7 +1206,7 @@ int chain_sm100(const StepSm100& s, cudaStream_t st) {
     if ((rc = map_terms(m.x, 3, x, rows[t], H, H))) return rc;
     if ((rc = map_terms(m.w1, 3, w1, P, H, H))) return rc;
     if ((rc = map_terms(m.h, 2, hh, rows[t], P, P))) return rc;
-    if ((rc = map_terms(m.w2, 2, w2, P, P, P))) return rc;
+    if ((rc = map_terms(m.w2, 2, w2, P, P, P, 64))) return rc;
     if ((rc = map_terms(m.dy, 2, dy, rows[t], P, P))) return rc;
     if ((rc = map_terms(m.w2t, 2, w2t, P, P, P))) return rc;
     if ((rc = map_terms(m.dyt, 2, dyt, P, rows[t], w.ldt))) return rc;
@@ -939,7 +1217,7 @@ int chain_sm100(const StepSm100& s, cudaStream_t st) {
     if ((rc = map_terms(m.w1t, 2, w1t, H, P, P))) return rc;
   }
   p.B = B; p.H = H; p.P = P;
-  p.RTB = (B + BM - 1) / BM; p.NC = (P + BN - 1) / BN; p.NCH = (H + BN - 1) / BN;
+  p.RTB = (B + BM - 1) / BM; p.NC = (P + BN - 1) / BN; p.NCH = (H + BN - 1) / BN; p.NCF = P / 64;
   p.ldt = w.ldt; p.dcol = w.dcol;
   p.pairs = x3 ? 3 : 1; p.terms = x3 ? 2 : 1;
   {
@@ -950,13 +1228,21 @@ int chain_sm100(const StepSm100& s, cudaStream_t st) {
   }
   for (int t = 0; t < 2; ++t) p.kbt[t] = (rows[t] + BK - 1) / BK;
   p.kcb = 8;
+  {
+    const char* e = getenv("TT_CHAIN_KCB");  // tuning hook: k-blocks (64 batch rows each) per weight-gradient chunk
+    if (e && atoi(e) >= 4) p.kcb = atoi(e) / 4 * 4;
+  }
   while ((p.kbt[0] + p.kcb - 1) / p.kcb + (p.kbt[1] + p.kcb - 1) / p.kcb > 48) p.kcb += 8;
   for (int t = 0; t < 2; ++t) p.nch[t] = (p.kbt[t] + p.kcb - 1) / p.kcb;
   const int grid = sm_count();
+  // the 3 * NCF loss tasks of one row tile wait for each other inside their epilogues: they must sit on distinct CTAs
+  TT_REQUIRE(grid >= 3 * (P / 64), "tt_triplet_step: projection dim %d needs %d co-resident CTAs, the device has %d SMs", P,
+             3 * (P / 64), grid);
   const int n_rt = 3 * p.RTB, nchs = p.nch[0] + p.nch[1];
   const int count[T_COUNT] = {grid,
+                              grid,
                               n_rt * p.NC,
-                              p.RTB * p.NC,
+                              n_rt * p.NCF,
                               n_rt * p.NC,
                               s.dxhat ? n_rt * p.NCH : 0,
                               nchs * p.NC * p.NC,
@@ -966,23 +1252,30 @@ int chain_sm100(const StepSm100& s, cudaStream_t st) {
   for (int k = 0; k < T_COUNT; ++k) p.off[k + 1] = p.off[k] + count[k];
   p.total_signals = (unsigned)(count[T_F2L] + count[T_DZ] + count[T_DW2] + count[T_DW1]);
   p.stages = chain_stages();
-  // weights of both towers -> bf16 terms (+ transposes for the backward contractions)
-  int tile0 = 0;
+  // weights of both towers -> bf16 terms (+ transposes for the backward contractions); the first-layer weights come
+  // first in the flat pass: layer 1 starts as soon as THEY are split (counter 0), the rest signals counter 2
+  int f4 = 0, t64 = 0;
   p.n_sj = 0;
   for (int t = 0; t < 2; ++t) {
     SplitJobC a{W1[t], w.w1_hi[t], w.w1_lo[t], x3 ? w.w1_lo2[t] : nullptr, s.dxhat ? w.w1t_hi[t] : nullptr,
-                s.dxhat ? w.w1t_lo[t] : nullptr, P, H, P, tile0, (H + 31) / 32};
-    tile0 += ((P + 31) / 32) * a.tiles_c;
+                s.dxhat ? w.w1t_lo[t] : nullptr, P, H, f4, s.dxhat ? t64 : -1, H / 64};
+    f4 += P * H / 4;
+    if (s.dxhat) t64 += (P / 64) * (H / 64);
     p.sj[p.n_sj++] = a;
-    SplitJobC b{W2[t], w.w2_hi[t], w.w2_lo[t], nullptr, w.w2t_hi[t], w.w2t_lo[t], P, P, P, tile0, (P + 31) / 32};
-    tile0 += ((P + 31) / 32) * b.tiles_c;
+  }
+  p.n_split_f4_w1 = f4;
+  for (int t = 0; t < 2; ++t) {
+    SplitJobC b{W2[t], w.w2_hi[t], w.w2_lo[t], nullptr, w.w2t_hi[t], w.w2t_lo[t], P, P, f4, t64, P / 64};
+    f4 += P * P / 4;
+    t64 += (P / 64) * (P / 64);
     p.sj[p.n_sj++] = b;
   }
-  p.n_split_tiles = tile0;
+  p.n_split_f4 = f4;
+  p.n_split_t64 = t64;
   p.margin = s.margin; p.inv_batch = s.inv_batch; p.grad_scale = s.grad_scale;
   p.b1[0] = s.bq1; p.b1[1] = s.bd1; p.b2[0] = s.bq2; p.b2[1] = s.bd2;
   const bool dbg = chain_debug_out() != 0;
-  p.h = s.h; p.y = dbg ? s.y : nullptr; p.dy = dbg ? s.dy : nullptr; p.dz1 = dbg ? w.dz1 : nullptr;
+  p.h = dbg ? s.h : nullptr; p.y = dbg ? s.y : nullptr; p.dy = dbg ? s.dy : nullptr; p.dz1 = dbg ? w.dz1 : nullptr;
   p.dxhat = s.dxhat; p.stats = s.stats; p.loss = s.loss;
   p.h_hi = w.h_hi; p.h_lo = w.h_lo; p.ht_hi = w.ht_hi; p.ht_lo = w.ht_lo;
   p.dy_hi = w.dy_hi; p.dy_lo = w.dy_lo; p.dyt_hi = w.dyt_hi; p.dyt_lo = w.dyt_lo;
@@ -991,8 +1284,15 @@ int chain_sm100(const StepSm100& s, cudaStream_t st) {
   p.part2 = w.partial2; p.part1 = w.partial;
   p.dW1[0] = s.dWq1; p.dW1[1] = s.dWd1; p.db1[0] = s.dbq1; p.db1[1] = s.dbd1;
   p.dW2[0] = s.dWq2; p.dW2[1] = s.dWd2; p.db2[0] = s.dbq2; p.db2[1] = s.dbd2;
-  p.stat_part = w.stat_part; p.cs1 = w.cs1; p.cs2 = w.cs2; p.hinge_part = w.hinge_part;
+  p.stat_part = w.stat_part; p.cs1 = w.cs1; p.cs2 = w.cs2; p.hinge_part = w.hinge_part; p.ybuf = w.ybuf;
   p.ctr = w.counters;
+  p.n_counters = w.n_counters;
+  p.nS = grid;
+  {
+    const char* e = getenv("TT_CHAIN_KROT");
+    p.krot = e ? atoi(e) : 0;  // off: no speed-up measured, and ascending k keeps the rounding correlated with the fp32 oracle
+  }
+  p.x_hi = w.x_hi; p.x_lo = w.x_lo; p.xt_hi = w.xt_hi; p.xt_lo = w.xt_lo;
   if (s.adam.param) {
     const FusedAdam& a = s.adam;
     TT_REQUIRE(a.state && a.grad && a.exp_avg && a.exp_avg_sq, "tt_triplet_step: fused Adam needs state, grad and both moments");
@@ -1008,8 +1308,24 @@ int chain_sm100(const StepSm100& s, cudaStream_t st) {
     p.adam_state = a.state; p.adam_p = a.param; p.adam_g = a.grad; p.adam_m = a.exp_avg; p.adam_v = a.exp_avg_sq;
     p.lr = a.lr; p.beta1 = a.beta1; p.beta2 = a.beta2; p.eps = a.eps;
   }
-  TT_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)w.n_counters * sizeof(unsigned), st));
-  chain_kernel<<<grid, kThreads, chain_smem(p.stages), st>>>(p);
+  {
+    const char* e = getenv("TT_CHAIN_TRACE");
+    p.trace = (e && atoi(e) != 0 && grid <= kTraceCtas) ? w.trace : nullptr;
+    if (p.trace) TT_CUDA(cudaMemsetAsync(w.trace, 0, (size_t)kTraceCtas * kTraceSlots * 16, st));
+  }
+  // (no memset of the counters: the workspace is zero-filled once by its owner and every launch leaves them at zero)
+  p.use_pdl = after_gather ? 1 : 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = chain_smem(p.stages);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.use_pdl ? 1 : 0;
+  TT_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, p));
   TT_LAUNCH_CHECK();
   return 0;
 }

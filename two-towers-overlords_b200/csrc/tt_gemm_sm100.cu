@@ -633,6 +633,10 @@ static int fwd1_products() {
   }
   return v;
 }
+static bool pdl_chain_enabled() {
+  const char* e = getenv("TT_CHAIN_PDL");  // tuning hook: 0 = plain stream order between the gather and the chain kernel
+  return e ? atoi(e) != 0 : true;
+}
 static int step_concurrency() {
   const char* e = getenv("TT_STEP_FORK");  // tuning hook: 0 = one serial chain
   return e ? atoi(e) : 1;
@@ -656,15 +660,17 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
 
   // 1. pooled gather: fp32 xhat + its bf16 split (row-major); the transposed copy comes from a tiled transpose
   const bool front = s.phases == 0 || (s.phases & TT_STEP_FRONT), back = s.phases == 0 || (s.phases & TT_STEP_BACK);
+  const bool chain = s.chain == 1 || (s.chain == 0 && chain_enabled());
   if (front) {
     PoolParams pp = s.pool;
     pp.x_hi = w.x_hi; pp.x_lo = w.x_lo; pp.x_lo2 = (np == 3) ? w.x_lo2 : nullptr; pp.xt_hi = nullptr; pp.xt_lo = nullptr;
     pp.share_sm = (s.phases == TT_STEP_FRONT) ? 1 : 0;  // gather-only call = the pipelined trainer's look-ahead gather
     if ((rc = pool_fwd_launch(pp, s.table_dtype, H, st))) return rc;
-    if ((rc = transpose_pair(w.x_hi, w.x_lo, 3 * B, H, w.xt_hi, w.xt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
+    // (the persistent chain kernel transposes the xhat terms itself)
+    if (!chain && (rc = transpose_pair(w.x_hi, w.x_lo, 3 * B, H, w.xt_hi, w.xt_lo, w.ldt, 0, B, w.dcol - B, st))) return rc;
   }
   if (!back) return 0;
-  if (chain_enabled()) return chain_sm100(s, st);
+  if (chain) return chain_sm100(s, /*after_gather=*/front && pdl_chain_enabled(), st);
   // 2. weights of both towers -> bf16 terms (+ transposes for the backward contractions), one launch
   {
     SplitJob jobs[4];

@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(kPoolThreads) pool_fwd_kernel(const PoolParams
   __shared__ int s_wc[kPoolWarps];
   __shared__ float s_fred[kPoolWarps];
 
+  // a programmatic dependent (the persistent chain kernel of a whole-step call) may start filling SMs as soon as the
+  // last wave of this grid is resident; it waits for this grid's completion before it reads xhat
+  pdl_launch();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // block -> (segment, sequence); host orders segments longest-first so short ones fill the tail

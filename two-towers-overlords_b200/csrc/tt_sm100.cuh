@@ -34,12 +34,13 @@ struct StepSm100 {
   size_t ws_bytes;
   int phases;                 // 0 / TT_STEP_FRONT | TT_STEP_BACK
   FusedAdam adam;
+  int chain;                  // 1 = persistent chain kernel, 2 = per-kernel chain, 0 = default (chain_enabled())
 };
 size_t step_sm100_ws_bytes(int B, int H, int P, int train_table);
 int step_sm100(const StepSm100& s, cudaStream_t st);
 // persistent chain kernel (tt_chain_sm100.cu): everything of the step after the pooled gather in ONE launch
 bool chain_enabled();  // TT_CHAIN=0 selects the per-kernel chain
-int chain_sm100(const StepSm100& s, cudaStream_t st);
+int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st);
 
 size_t scan_sm100_ws_bytes(int Q, long long N, int P, int k);
 int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void* Db, int Q, long long N, int P, int k,

@@ -20,10 +20,12 @@ struct StepWs {
   float *dz1, *partial, *partial2, *colsum, *colsum2, *loss_scratch;
   // persistent chain kernel (tt_chain_sm100.cu): per-(triplet tile, column half) loss partial sums, per-row-tile
   // column sums for the bias gradients, per-tile hinge sums, dependency counters
-  float *stat_part, *cs1, *cs2, *hinge_part;
+  float *stat_part, *cs1, *cs2, *hinge_part, *ybuf;
   unsigned* counters;
   int n_counters;
+  unsigned long long* trace;  // TT_CHAIN_TRACE=1: [CTA][kTraceSlots] x {task index << 1 | end, globaltimer ns}
 };
+constexpr int kTraceSlots = 64, kTraceCtas = 160;
 
 static inline size_t carve_step(char* base, int B, int H, int P, int train_table, StepWs* out) {
   char* p = base;
@@ -54,12 +56,14 @@ static inline size_t carve_step(char* base, int B, int H, int P, int train_table
   w.loss_scratch = ws_take<float>(p, (size_t)(B + 3) / 4 + 8);
   {
     const int RTB = (B + 127) / 128, NC = (P + 127) / 128;
-    w.stat_part = ws_take<float>(p, (size_t)RTB * 2 * NC * 5 * 128);
+    w.stat_part = ws_take<float>(p, (size_t)RTB * 2 * (P / 64 + 1) * 5 * 128);
     w.cs1 = ws_take<float>(p, (size_t)3 * RTB * P);
-    w.cs2 = ws_take<float>(p, (size_t)2 * RTB * P);
+    w.cs2 = ws_take<float>(p, (size_t)3 * RTB * P);
+    w.ybuf = ws_take<float>(p, (size_t)3 * RTB * 128 * P);  // layer-2 outputs exchanged between the q | p | n tasks
     w.hinge_part = ws_take<float>(p, (size_t)RTB + 8);
-    w.n_counters = 10 * RTB + 8;
+    w.n_counters = 10 * RTB + 8 + RTB * (P / 64 + 1);
     w.counters = ws_take<unsigned>(p, (size_t)w.n_counters);
+    w.trace = ws_take<unsigned long long>(p, (size_t)kTraceCtas * kTraceSlots * 2);
   }
   (void)train_table;
   if (out) *out = w;

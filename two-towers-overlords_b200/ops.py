@@ -211,6 +211,7 @@ class TripletStep:
         self.slots = []
         self._keep = []
         self._adam = None
+        self.chain = 0
 
     def bind(self, tokens, tables, params, grads, margin, inv_batch, grad_scale=1.0, table_grads=None):
         """tokens = (q_ids,q_mask,p_ids,p_mask,n_ids,n_mask) CUDA tensors; tables = (table_q, table_d);
@@ -241,6 +242,7 @@ class TripletStep:
             a.dtable_q, a.dtable_d = None, None
         a.precision, a.ws, a.ws_bytes = self.prec, N.ptr(self.ws), self.ws_bytes
         a.adam_param = None
+        a.chain = self.chain
         self.slots = [a]
         self._keep = [(tokens, tables, params, grads, table_grads)]
 
@@ -280,8 +282,43 @@ class TripletStep:
         """xhat [3B,H]: pooled + L2-normalised rows of the last run."""
         return self._views()["xhat"]
 
+    def internal(self, name: str, rows: int, cols: int, dtype=torch.bfloat16) -> torch.Tensor:
+        """View of a named internal buffer of a tensor-core step workspace (tt_debug_step_buffer)."""
+        B, Lq, Ld, H, P, vocab = self.shape
+        ptr = ctypes.c_void_p()
+        N.check(self.lib.tt_debug_step_buffer(N.ptr(self.ws), B, Lq, Ld, H, P, vocab, self.prec, int(self.train_table),
+                                              name.encode(), ctypes.byref(ptr)), "tt_debug_step_buffer")
+        off = ptr.value - self.ws.data_ptr()
+        nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
+        return self.ws[off: off + nbytes].view(dtype).view(rows, cols)
+
+    def set_chain(self, mode: int):
+        """tt_step_args.chain: 0 = library default (TT_CHAIN env, else the persistent kernel), 1 = persistent chain
+        kernel, 2 = one kernel per contraction."""
+        self.chain = int(mode)
+        for a in self.slots:
+            a.chain = self.chain
+
+    def chain_active(self) -> bool:
+        """True when tt_triplet_step runs the persistent chain kernel for this step."""
+        if self.prec == N.PRECISIONS["fp32"]:
+            return False
+        if self.chain:
+            return self.chain == 1
+        return os.environ.get("TT_CHAIN", "1") != "0"
+
+    def hidden(self) -> torch.Tensor:
+        """h [3B,P] fp32 of the last run.  The persistent chain kernel keeps h only as its bf16 terms (hi + lo)."""
+        if self.chain_active() and os.environ.get("TT_CHAIN_FP32_OUT", "0") == "0":
+            B, P = self.shape[0], self.shape[4]
+            return self.internal("h_hi", 3 * B, P).float() + self.internal("h_lo", 3 * B, P).float()
+        return self._views()["h"]
+
     def relu_gate(self) -> torch.Tensor:
         """bool [3B,P]: which hidden units the last run treated as active (h > 0) — the ReLU gate of its backward."""
+        if self.chain_active():
+            B, P = self.shape[0], self.shape[4]
+            return self.internal("h_hi", 3 * B, P).float() > 0
         return self._views()["h"] > 0
 
     def bind_adam(self, state, param, grad, exp_avg, exp_avg_sq, lr, betas, eps):

@@ -212,6 +212,16 @@ class FusedTrainer:
                                 torch.zeros_like(dt.pretrained_model.table, dtype=torch.float32))
         # TWO step workspaces: the pooled gather of step i+1 (tokens + frozen tables only, never the projection
         # weights) runs beside everything else of step i, so consecutive steps alternate between them
+        # How the projection chain is launched (tt_step_args.chain).  The persistent kernel is the shorter chain
+        # (~135 vs ~170 us alone at configs[1]) but wants every SM, so nothing runs beside it; the per-kernel chain
+        # lets the look-ahead gather of the next step slip between its small kernels.  Measured on one B200:
+        # single GPU 0.249 ms/step per-kernel + look-ahead vs 0.258 persistent; with data parallelism the gather
+        # runs beside the exchange kernel instead, and the persistent chain wins.  TT_CHAIN=1/0 forces either.
+        env_chain = os.environ.get("TT_CHAIN")
+        if env_chain is not None:
+            self.chain_mode = 1 if env_chain != "0" else 2
+        else:
+            self.chain_mode = 1 if (world_size > 1 or self.train_table) else 2
         self.step_objs = []
         for _ in range(2):
             so = ops.TripletStep(batch_size, Lq, Ld, self.H, self.P, self.vocab, self.precision, dev,
@@ -221,6 +231,7 @@ class FusedTrainer:
                     self.g_views, self.margin, 1.0 / (batch_size * world_size), 1.0, self.table_grads)
             for toks in self.tok_slots[1:]:
                 so.add_tokens(toks)
+            so.set_chain(self.chain_mode)
             if self.exchange == "none" and self.world == 1:
                 # single GPU: torch.optim.Adam rides inside the step call (the tail of the persistent chain kernel
                 # with the tensor-core precisions; a launch after the step otherwise)
@@ -301,16 +312,42 @@ class FusedTrainer:
         The gather is bandwidth work on many small CTAs, the rest is a chain of latency-bound tensor-core kernels:
         side by side the gather disappears behind the chain (bench: 287 -> 182 us per step on one B200)."""
         cur = torch.cuda.current_stream()
+        fused_opt = self.xchg is None and self.world == 1
+        if self._whole_step():
+            # ONE call = pooled gather -> persistent chain kernel (+ Adam in its tail): two launches, the second a
+            # programmatic dependent of the first
+            self._fwd_bwd(slot, 0, parity, optimise=fused_opt)
+            return
+        chain_mode = self.step_objs[0].chain_active()
+        if not chain_mode:
+            # per-kernel chain: many small latency-bound kernels, the look-ahead gather's CTAs slip in between them
+            if next_slot is not None:
+                self.side.wait_stream(cur)
+                with torch.cuda.stream(self.side):
+                    self._fwd_bwd(next_slot, 1, parity ^ 1)
+            self._fwd_bwd(slot, 2, parity, optimise=fused_opt)
+            if self.xchg is not None:
+                self._exchange()
+            if next_slot is not None:
+                cur.wait_stream(self.side)
+            return
+        # Persistent chain kernel + data parallelism: the chain wants one CTA on EVERY SM (its CTAs wait for each other),
+        # so nothing runs beside it; the look-ahead gather runs beside the exchange kernel instead, which spends most
+        # of its time waiting for the peers' gradient flags on one small CTA per SM.
+        self._fwd_bwd(slot, 2, parity, optimise=fused_opt)
         if next_slot is not None:
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
                 self._fwd_bwd(next_slot, 1, parity ^ 1)
-        fused_opt = self.xchg is None and self.world == 1
-        self._fwd_bwd(slot, 2, parity, optimise=fused_opt)
         if self.xchg is not None:
             self._exchange()
         if next_slot is not None:
             cur.wait_stream(self.side)
+
+    def _whole_step(self) -> bool:
+        """Single GPU with the persistent chain kernel: a step is gather -> chain in one stream, no look-ahead."""
+        return (self.xchg is None and self.world == 1 and self.step_objs[0].chain_active()
+                and os.environ.get("TT_STEP_ORDER", "whole") == "whole")
 
     def wait(self):
         """Kept for API symmetry: every step() leaves parameters and `loss_view` final in stream order."""
@@ -381,6 +418,9 @@ class FusedTrainer:
         if not self._warm:
             self._warm_up()
         for s_ in range(n):
+            if self._whole_step():
+                self._graph(s_, None, self._parity)  # whole-step graphs: no look-ahead, one workspace
+                continue
             nxt = (s_ + 1) % n
             for parity in ((s_ & 1,) if n % 2 == 0 else (0, 1)):
                 self._graph(s_, nxt, parity)
@@ -395,6 +435,10 @@ class FusedTrainer:
         if self.train_table:
             next_slot = None  # a trainable table changes between steps: its gather cannot run ahead of the update
         lib = ops.N.load()
+        whole = self._whole_step()
+        if whole:
+            next_slot = None  # the gather of THIS step is part of the step's graph
+            self._primed = slot
         if self._primed != slot:  # pipeline start (or a schedule change): this step's gather has not run yet
             # nothing is primed, so the workspace is free to choose: make it a function of the slot, which is what
             # prepare() captured for an even slot count (a restart must never land on an uncaptured graph key)
