@@ -455,6 +455,7 @@ def run_b200(args):
     trainer.close()
     del trainer, model
     torch.cuda.empty_cache()
+    chain_variant = run_chain_variant(dev, args, ids_dtype, mask_dtype, host_packed) if (world == 1 and not args.no_chain_variant) else None
     config2 = run_config2(dev, world, rank, args) if not args.no_config2 else None
     epoch_leg = run_epoch_leg(dev, world, rank, args) if not args.no_epoch else None
     torch.cuda.empty_cache()
@@ -473,7 +474,7 @@ def run_b200(args):
             "variant": {"projection_precision": args.precision, "table_dtype": args.table_dtype,
                         "dp_exchange": exchange_kind, "token_dtypes": f"ids {args.ids_dtype}, mask u8"},
             "graph_captures_in_timed_region": captures_in_timed, "dp_check": dp_check, "config2": config2,
-            "epoch_leg": epoch_leg,
+            "epoch_leg": epoch_leg, "projection_chain": chain_variant,
             "dp_exchange_us": exchange_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
@@ -483,6 +484,78 @@ def run_b200(args):
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# the projection chain, both ways of launching it (tt_step_args.chain)
+# --------------------------------------------------------------------------------------------------
+def run_chain_variant(dev, args, ids_dtype, mask_dtype, host_packed, steps=40):
+    """configs[1] on one GPU: everything after the pooled gather (both layers of both towers, loss, backward, bias
+    sums, gradient reduction, Adam) as ONE persistent tcgen05 kernel vs one kernel per contraction — each timed alone
+    (gather already done, CUDA events around back-to-back launches) and as a whole training step.  Tensor roofline of
+    the chain: useful flops (7.08 MFLOP per triplet) / time against the sustained bf16 peak; the
+    split-bf16 arithmetic issues 3 (6 in layer 1) bf16 products per useful one."""
+    from two_towers_overlords_b200 import TwoTowersModel
+    from two_towers_overlords_b200.training import FusedTrainer
+
+    _, tensor_peak, peak_kind = peaks()
+    flops = B_PER_GPU * 3 * ((768 * P_DIM + 2 * P_DIM * P_DIM) + (4 * P_DIM * P_DIM + 768 * P_DIM))
+    issued = B_PER_GPU * 3 * ((6 * 768 * P_DIM + 3 * 2 * P_DIM * P_DIM) + 3 * (4 * P_DIM * P_DIM + 768 * P_DIM))
+    out = {"workload": "configs[1] projection chain per step: 3 x 2048 rows, 384 -> 512 -> 512, cosine triplet loss, "
+                       "backward, Adam", "useful_gflop": flops / 1e9, "issued_bf16_gflop": issued / 1e9}
+    prev = os.environ.get("TT_CHAIN")
+    try:
+        for name, flag in (("persistent_kernel", "1"), ("kernel_per_contraction", "0")):
+            os.environ["TT_CHAIN"] = flag
+            torch.manual_seed(0)
+            model = TwoTowersModel(projection_dim=P_DIM, precision=args.precision).to(dev)
+            tr = FusedTrainer(model, MARGIN, LR, B_PER_GPU, LQ, LD, precision=args.precision, ids_dtype=ids_dtype,
+                              mask_dtype=mask_dtype, token_slots=8)
+            for slot in range(8):
+                tr.load_packed(host_packed[slot], slot)
+            tr.prepare()
+            for i in range(8):
+                tr.step(i % 8, (i + 1) % 8)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(steps):
+                tr.step(i % 8, (i + 1) % 8)
+            ev1.record()
+            torch.cuda.synchronize()
+            step_ms = ev0.elapsed_time(ev1) / steps
+            launches = int(tr.kernel_launches_per_step or 0)
+            # the chain alone: the gather of slot 0 sits in workspace 0, launch its back half repeatedly (gradients
+            # only — eager launches; the per-kernel chain forks its independent branches onto library streams)
+            tr._fwd_bwd(0, 1, 0)
+            for _ in range(3):
+                tr._fwd_bwd(0, 2, 0)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(steps):
+                tr._fwd_bwd(0, 2, 0)
+            ev1.record()
+            torch.cuda.synchronize()
+            alone_us = ev0.elapsed_time(ev1) / steps * 1e3
+            out[name] = {"step_ms": step_ms, "triplets_per_s": B_PER_GPU / (step_ms * 1e-3),
+                         "launches_per_step": launches, "chain_alone_us": alone_us,
+                         "roofline": {"bound": "tensor", "achieved": flops / (alone_us * 1e-6) / 1e12, "peak": tensor_peak,
+                                      "peak_kind": peak_kind, "unit": "TFLOP/s",
+                                      "frac": flops / (alone_us * 1e-6) / 1e12 / tensor_peak,
+                                      "issued_frac": issued / (alone_us * 1e-6) / 1e12 / tensor_peak, "traffic": None}}
+            tr.close()
+            del tr, model
+            torch.cuda.empty_cache()
+    finally:
+        if prev is None:
+            os.environ.pop("TT_CHAIN", None)
+        else:
+            os.environ["TT_CHAIN"] = prev
+    out["note"] = ("the persistent kernel is the shorter chain but holds every SM (one 320-thread CTA with ~210 KB of "
+                   "shared memory each), so the look-ahead gather cannot run beside it; FusedTrainer therefore keeps "
+                   "one kernel per contraction when there is a look-ahead gather to overlap and uses the persistent "
+                   "kernel for whole-step calls (trainable tables)")
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -622,7 +695,7 @@ def run_config2(dev, world, rank, args, B=4096, P=384, steps=12):
         "metric": METRIC, "value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
         "gpu_launches_per_step": int(launches), "n_gpus": world, "scaling": "replicas (no exchange in this leg)",
         "roofline_pool_bwd": {
-            "kernel": "tt_pool_bwd (document table: 2B x 256 tokens -> radix sort by id -> one warp per touched row)",
+            "kernel": "tt_pool_bwd (document table: 2B x 256 tokens -> stable radix sort by id -> one warp per touched row, rows named by > 256 tokens cut into 2048-entry chunks summed in a fixed order)",
             "bound": "hbm", "achieved": alg / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "peak_kind": peak_kind,
             "unit": "GB/s", "frac": alg / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_call": bwd_ms,
             "launches_per_call": int(bwd_launches), "algorithmic_bytes_per_call": alg, "unique_rows": n_unique,
@@ -844,6 +917,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-scan", action="store_true")
     ap.add_argument("--no-config2", action="store_true", help="skip the configs[2] leg (trainable tables, B=4096, P=384)")
+    ap.add_argument("--no-chain-variant", action="store_true", help="skip the projection-chain leg (persistent kernel vs one kernel per contraction)")
     ap.add_argument("--no-epoch", action="store_true", help="skip the configs[3] leg (~800k-triplet pass + NDCG@10)")
     ap.add_argument("--epoch-triplets", type=int, default=800_000)
     ap.add_argument("--scan-docs", type=int, default=8_800_000)

@@ -70,7 +70,7 @@ __global__ void pool_bwd_prep_kernel(const float* __restrict__ dxhat, const floa
 
 // ---- 2. radix sort -----------------------------------------------------------------------------
 __global__ void make_keys_kernel(const BwdSegs S, int vocab, long long N, unsigned* __restrict__ keys,
-                                 unsigned* __restrict__ vals, int* __restrict__ id_count) {
+                                 unsigned* __restrict__ vals) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int s = seg_of(S, i);
@@ -82,7 +82,16 @@ __global__ void make_keys_kernel(const BwdSegs S, int vocab, long long N, unsign
   }
   keys[i] = key;
   vals[i] = (unsigned)i;
-  atomicAdd(&id_count[key], 1);  // integer counts: order-independent
+}
+
+// id_off[k] = number of sorted keys < k, for k in [0, vocab + 1]: read off the run boundaries of the sorted keys (no
+// atomics: a Zipf head or the masked-token sentinel would put millions of increments on one address)
+__global__ void id_offsets_kernel(const unsigned* __restrict__ keys, long long N, int vocab, int* __restrict__ id_off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > N) return;
+  const int prev = i == 0 ? -1 : (int)keys[i - 1];
+  const int cur = i == N ? vocab + 1 : (int)keys[i];
+  for (int k = prev + 1; k <= cur; ++k) id_off[k] = (int)i;
 }
 
 __global__ void __launch_bounds__(kSortBlockWarps * 32) radix_hist_kernel(const unsigned* __restrict__ keys,
@@ -103,40 +112,73 @@ __global__ void __launch_bounds__(kSortBlockWarps * 32) radix_hist_kernel(const 
     for (int d = lane; d < 256; d += 32) hist[(size_t)d * W + w] = s_h[warp][d];
 }
 
-// exclusive scan of n ints, single CTA
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int* __restrict__ data, long long n) {
-  __shared__ long long s_tot[1024];
-  const int t = threadIdx.x;
-  const long long per = (n + 1023) / 1024;
-  const long long beg = min((long long)t * per, n), end = min(beg + per, n);
-  long long sum = 0;
-  for (long long i = beg; i < end; ++i) sum += data[i];
-  s_tot[t] = sum;
+// hist[d][0..W) -> exclusive prefix within digit d (in place), tot[d] = the digit's total.  One CTA per digit.
+__global__ void __launch_bounds__(1024) digit_scan_kernel(int* __restrict__ hist, int W, int* __restrict__ tot) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  int* h = hist + (size_t)blockIdx.x * W;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_carry = 0;
   __syncthreads();
-  // Hillis-Steele over 1024 partials
-  for (int off = 1; off < 1024; off <<= 1) {
-    long long v = (t >= off) ? s_tot[t - off] : 0;
+  for (int base = 0; base < W; base += 1024) {
+    const int i = base + t;
+    const int v = i < W ? h[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    s_tot[t] += v;
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int before = (warp ? s_warp[warp - 1] : 0) + carry;
+    if (i < W) h[i] = before + x - v;
+    __syncthreads();
+    if (t == 1023) s_carry = carry + s_warp[31];
     __syncthreads();
   }
-  long long run = s_tot[t] - sum;
-  for (long long i = beg; i < end; ++i) {
-    const int v = data[i];
-    data[i] = (int)run;
-    run += v;
-  }
+  if (t == 0) tot[blockIdx.x] = s_carry;
 }
 
 __global__ void __launch_bounds__(kSortBlockWarps * 32)
     radix_scatter_kernel(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in, long long N,
-                         int shift, int W, const int* __restrict__ hist, unsigned* __restrict__ keys_out,
-                         unsigned* __restrict__ vals_out) {
+                         int shift, int W, const int* __restrict__ hist, const int* __restrict__ tot,
+                         unsigned* __restrict__ keys_out, unsigned* __restrict__ vals_out) {
   __shared__ int s_off[kSortBlockWarps][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * kSortBlockWarps + warp;
   if (w >= W) return;
-  for (int d = lane; d < 256; d += 32) s_off[warp][d] = hist[(size_t)d * W + w];
+  {  // first slot of digit d for this warp = (sum of the totals of smaller digits) + (this warp's prefix inside d)
+    int t8[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      t8[k] = tot[lane * 8 + k];
+      sum += t8[k];
+    }
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    int run = x - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s_off[warp][lane * 8 + k] = run + hist[(size_t)(lane * 8 + k) * W + w];
+      run += t8[k];
+    }
+  }
   __syncwarp();
   const long long beg = (long long)w * kSortWarpItems;
   const long long end = min(beg + (long long)kSortWarpItems, N);
@@ -193,18 +235,35 @@ __device__ __forceinline__ void run_sum(const BwdSegs& S, const unsigned* __rest
   }
 }
 
+constexpr int kChunk = 2048;  // entries of a heavy row summed by one CTA
+
+// heavy bookkeeping (ints): [0] number of heavy ids, [1] number of chunks, then per heavy id {id, first chunk, chunks},
+// then per chunk {id, index of the chunk inside its row}
 template <int NV>
 __global__ void __launch_bounds__(256)
     seg_reduce_kernel(const BwdSegs S, const unsigned* __restrict__ vals, const int* __restrict__ id_off, int vocab,
-                      const float* __restrict__ g, float* __restrict__ dtable, int accumulate,
-                      int* __restrict__ heavy_list, int* __restrict__ heavy_count) {
+                      const float* __restrict__ g, float* __restrict__ dtable, int accumulate, int* __restrict__ hv,
+                      int max_heavy) {
   constexpr int H = NV * 128;
   const int id = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (id >= vocab) return;
   const long long beg = id_off[id], end = id_off[id + 1];
   if (end - beg > kHeavy) {
-    if (lane == 0) heavy_list[atomicAdd(heavy_count, 1)] = id;
+    // rows named by many tokens (Zipf heads, [CLS]/[SEP]) are cut into chunks of kChunk entries, one CTA each; which
+    // slots a row gets depends on scheduling, the summation order (chunk order, fixed split inside a chunk) does not
+    if (lane == 0) {
+      const int nch = (int)((end - beg + kChunk - 1) / kChunk);
+      const int h = atomicAdd(&hv[0], 1);
+      const int base = atomicAdd(&hv[1], nch);
+      int* rec = hv + 2 + 3 * h;
+      rec[0] = id; rec[1] = base; rec[2] = nch;
+      int* ch = hv + 2 + 3 * max_heavy;
+      for (int c = 0; c < nch; ++c) {
+        ch[2 * (base + c)] = id;
+        ch[2 * (base + c) + 1] = c;
+      }
+    }
     return;
   }
   float acc[NV * 4];
@@ -224,20 +283,22 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// stage 1: one CTA per chunk; warp w sums a fixed 32-aligned slice, the eight slices are added in warp order
 template <int NV>
 __global__ void __launch_bounds__(256)
-    seg_reduce_heavy_kernel(const BwdSegs S, const unsigned* __restrict__ vals, const int* __restrict__ id_off,
-                            const float* __restrict__ g, float* __restrict__ dtable, int accumulate,
-                            const int* __restrict__ heavy_list, const int* __restrict__ heavy_count) {
+    heavy_chunk_kernel(const BwdSegs S, const unsigned* __restrict__ vals, const int* __restrict__ id_off,
+                       const float* __restrict__ g, const int* __restrict__ hv, int max_heavy,
+                       float* __restrict__ partial) {
   constexpr int H = NV * 128;
   __shared__ __align__(16) float s_part[8][H];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_heavy = *heavy_count;
-  for (int hi = blockIdx.x; hi < n_heavy; hi += gridDim.x) {
-    const int id = heavy_list[hi];
-    const long long beg = id_off[id], end = id_off[id + 1];
-    // fixed split: warp w owns a 32-aligned slice -> the summation order does not depend on scheduling
-    const long long per = (((end - beg) + 7) / 8 + 31) / 32 * 32;
+  const int n_chunks = hv[1];
+  const int* ch = hv + 2 + 3 * max_heavy;
+  for (int slot = blockIdx.x; slot < n_chunks; slot += gridDim.x) {
+    const int id = ch[2 * slot], c = ch[2 * slot + 1];
+    const long long beg = (long long)id_off[id] + (long long)c * kChunk;
+    const long long end = min((long long)id_off[id + 1], beg + kChunk);
+    constexpr long long per = kChunk / 8;
     const long long b = min(beg + warp * per, end), e = min(b + per, end);
     float acc[NV * 4];
 #pragma unroll
@@ -248,27 +309,58 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<float4*>(&s_part[warp][(k * 32 + lane) * 4]) =
           make_float4(acc[k * 4], acc[k * 4 + 1], acc[k * 4 + 2], acc[k * 4 + 3]);
     __syncthreads();
-    for (int c = threadIdx.x; c < H; c += 256) {
+    for (int col = threadIdx.x; col < H; col += 256) {
       float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) sum += s_part[w][c];
-      float* dst = dtable + (size_t)id * H + c;
-      *dst = accumulate ? (*dst + sum) : sum;
+      for (int w = 0; w < 8; ++w) sum += s_part[w][col];
+      partial[(size_t)slot * H + col] = sum;
     }
     __syncthreads();
   }
 }
 
+// stage 2: one warp per heavy row adds its chunk sums in chunk order
+template <int NV>
+__global__ void __launch_bounds__(256)
+    heavy_final_kernel(const int* __restrict__ hv, const float* __restrict__ partial, float* __restrict__ dtable,
+                       int accumulate) {
+  constexpr int H = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int n_heavy = hv[0];
+  for (int h = blockIdx.x * 8 + (threadIdx.x >> 5); h < n_heavy; h += gridDim.x * 8) {
+    const int id = hv[2 + 3 * h], base = hv[2 + 3 * h + 1], nch = hv[2 + 3 * h + 2];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < nch; ++c) {
+        const float4 t = *(reinterpret_cast<const float4*>(partial + (size_t)(base + c) * H) + k * 32 + lane);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      float4* dst = reinterpret_cast<float4*>(dtable + (size_t)id * H) + k * 32 + lane;
+      if (accumulate) {
+        const float4 old = *dst;
+        acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+      }
+      *dst = acc;
+    }
+  }
+}
+
 }  // namespace
+
+static inline long long max_heavy_rows(long long n_tokens) { return n_tokens / kHeavy + 1; }
+static inline long long max_heavy_chunks(long long n_tokens) { return n_tokens / kChunk + max_heavy_rows(n_tokens); }
 
 size_t pool_bwd_ws_bytes(long long n_tokens, int vocab) {
   const long long W = (n_tokens + kSortWarpItems - 1) / kSortWarpItems;
   size_t b = 0;
   b += 4 * ws_round((size_t)n_tokens * 4);         // keys A/B, vals A/B
   b += ws_round((size_t)256 * (W + 1) * 4);        // digit histograms
-  b += ws_round((size_t)(vocab + 2) * 4);          // id counts / offsets
-  b += ws_round((size_t)(vocab + 1) * 4);          // heavy list + counter
-  return b + 1024;
+  b += ws_round((size_t)256 * 4);                  // digit totals
+  b += ws_round((size_t)(vocab + 2) * 4);          // id offsets
+  b += ws_round((size_t)(2 + 3 * max_heavy_rows(n_tokens) + 2 * max_heavy_chunks(n_tokens)) * 4);  // heavy bookkeeping
+  b += ws_round((size_t)max_heavy_chunks(n_tokens) * 768 * 4);  // chunk sums (H <= 768)
+  return b + 2048;
 }
 
 int pool_bwd_prep(const float* dxhat, const float* xhat, const float* cnt, const float* nrm, int rows, int H,
@@ -310,14 +402,15 @@ int pool_bwd_scatter(const PoolBwdSeg* segs, int nseg, int ids_dtype, int mask_d
   unsigned* valA = ws_take<unsigned>(p, N);
   unsigned* valB = ws_take<unsigned>(p, N);
   int* hist = ws_take<int>(p, (size_t)256 * (W + 1));
-  int* id_cnt = ws_take<int>(p, vocab + 2);
-  int* heavy = ws_take<int>(p, vocab + 1);
-  int* heavy_count = heavy + vocab;
+  int* tot = ws_take<int>(p, 256);
+  int* id_off = ws_take<int>(p, vocab + 2);
+  const int max_heavy = (int)max_heavy_rows(N);
+  int* hv = ws_take<int>(p, (size_t)2 + 3 * max_heavy + 2 * max_heavy_chunks(N));
+  float* partial = ws_take<float>(p, (size_t)max_heavy_chunks(N) * H);
 
-  TT_CUDA(cudaMemsetAsync(id_cnt, 0, (size_t)(vocab + 2) * 4, st));
-  TT_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
+  TT_CUDA(cudaMemsetAsync(hv, 0, 8, st));
   if (N > 0) {
-    make_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, vocab, N, keyA, valA, id_cnt);
+    make_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, vocab, N, keyA, valA);
     TT_LAUNCH_CHECK();
     int bits = 1;
     while ((1ll << bits) < (long long)vocab + 1) ++bits;
@@ -326,24 +419,24 @@ int pool_bwd_scatter(const PoolBwdSeg* segs, int nseg, int ids_dtype, int mask_d
     for (int ps = 0; ps < passes; ++ps) {
       radix_hist_kernel<<<blocks, kSortBlockWarps * 32, 0, st>>>(keyA, N, ps * 8, W, hist);
       TT_LAUNCH_CHECK();
-      exclusive_scan_kernel<<<1, 1024, 0, st>>>(hist, (long long)256 * W);
+      digit_scan_kernel<<<256, 1024, 0, st>>>(hist, W, tot);
       TT_LAUNCH_CHECK();
-      radix_scatter_kernel<<<blocks, kSortBlockWarps * 32, 0, st>>>(keyA, valA, N, ps * 8, W, hist, keyB, valB);
+      radix_scatter_kernel<<<blocks, kSortBlockWarps * 32, 0, st>>>(keyA, valA, N, ps * 8, W, hist, tot, keyB, valB);
       TT_LAUNCH_CHECK();
       unsigned* t = keyA; keyA = keyB; keyB = t;
       t = valA; valA = valB; valB = t;
     }
   }
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(id_cnt, (long long)vocab + 2);
+  id_offsets_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(keyA, N, vocab, id_off);
   TT_LAUNCH_CHECK();
   const int rblocks = (vocab + 7) / 8;
-  const int hblocks = 296;
+  const int hblocks = 4 * sm_count();
 #define TT_SEG_CASE(NV)                                                                                         \
-  seg_reduce_kernel<NV><<<rblocks, 256, 0, st>>>(S, valA, id_cnt, vocab, g, dtable, accumulate, heavy,          \
-                                                 heavy_count);                                                  \
+  seg_reduce_kernel<NV><<<rblocks, 256, 0, st>>>(S, valA, id_off, vocab, g, dtable, accumulate, hv, max_heavy);   \
   TT_LAUNCH_CHECK();                                                                                            \
-  seg_reduce_heavy_kernel<NV><<<hblocks, 256, 0, st>>>(S, valA, id_cnt, g, dtable, accumulate, heavy,           \
-                                                       heavy_count);                                            \
+  heavy_chunk_kernel<NV><<<hblocks, 256, 0, st>>>(S, valA, id_off, g, hv, max_heavy, partial);                    \
+  TT_LAUNCH_CHECK();                                                                                            \
+  heavy_final_kernel<NV><<<sm_count(), 256, 0, st>>>(hv, partial, dtable, accumulate);                            \
   TT_LAUNCH_CHECK();
   switch (H / 128) {
     case 1: { TT_SEG_CASE(1) } break;

@@ -213,15 +213,16 @@ class FusedTrainer:
         # TWO step workspaces: the pooled gather of step i+1 (tokens + frozen tables only, never the projection
         # weights) runs beside everything else of step i, so consecutive steps alternate between them
         # How the projection chain is launched (tt_step_args.chain).  The persistent kernel is the shorter chain
-        # (~135 vs ~170 us alone at configs[1]) but wants every SM, so nothing runs beside it; the per-kernel chain
-        # lets the look-ahead gather of the next step slip between its small kernels.  Measured on one B200:
-        # single GPU 0.249 ms/step per-kernel + look-ahead vs 0.258 persistent; with data parallelism the gather
-        # runs beside the exchange kernel instead, and the persistent chain wins.  TT_CHAIN=1/0 forces either.
+        # (135 vs 171 us alone at configs[1], 2 launches per step instead of 18) but wants every SM, so nothing runs
+        # beside it; the per-kernel chain lets the look-ahead gather of the next step slip between its small kernels,
+        # and that overlap is worth more: measured on B200 0.249 vs 0.258 ms/step on one GPU, 0.274 vs 0.291 at N = 2.
+        # A trainable table has no look-ahead (the gather reads the table the step updates): persistent there.
+        # TT_CHAIN=1 / 0 forces either.
         env_chain = os.environ.get("TT_CHAIN")
         if env_chain is not None:
             self.chain_mode = 1 if env_chain != "0" else 2
         else:
-            self.chain_mode = 1 if (world_size > 1 or self.train_table) else 2
+            self.chain_mode = 1 if self.train_table else 2
         self.step_objs = []
         for _ in range(2):
             so = ops.TripletStep(batch_size, Lq, Ld, self.H, self.P, self.vocab, self.precision, dev,
