@@ -310,6 +310,36 @@ int tt_assemble_triplets(const tt_token_bank* qbank, const tt_token_bank* dbank,
  * launch with CUDA events: GB/s = bytes * iters / seconds.  This is the ceiling of the pooled gather, whose token
  * tables stay resident in L2 (the reference's counterpart is nn.Embedding inside backend/model.py:51-52).
  * ctas_per_sm <= 0 selects 8 (x 256 threads).  sink: 4 writable bytes. */
+/* ------------------------------------------------------------------------------------------
+ * The reference's full backbone: the frozen MiniLM-L6 BertModel of backend/model.py:24,
+ * run forward-only under no_grad at backend/model.py:51-52; output[0] = last hidden state.
+ * All pointers are device pointers.  Weight matrices are torch Linear weights [out, in] given as their
+ * bf16 (hi, lo) terms (tt_split_bf16_terms, once: the backbone is frozen); wqkv = rows of query | key | value.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tt_encoder_layer {
+  const void *wqkv_hi, *wqkv_lo; const float* bqkv;      /* [3H, H], [3H] */
+  const void *wo_hi, *wo_lo;     const float* bo;        /* [H, H], [H]   */
+  const float *ln1_g, *ln1_b;                            /* attention.output.LayerNorm */
+  const void *w1_hi, *w1_lo;     const float* b1;        /* intermediate.dense [I, H]  */
+  const void *w2_hi, *w2_lo;     const float* b2;        /* output.dense [H, I]        */
+  const float *ln2_g, *ln2_b;                            /* output.LayerNorm           */
+} tt_encoder_layer;
+typedef struct tt_encoder_weights {
+  const float *word_emb, *pos_emb, *type_emb;            /* [vocab,H], [max_pos,H], row 0 of [2,H] */
+  const float *emb_ln_g, *emb_ln_b;
+  int vocab, max_pos, hidden, heads, inter, n_layers;
+  float ln_eps;
+  const tt_encoder_layer* layers;                        /* HOST array of n_layers entries */
+} tt_encoder_weights;
+size_t tt_encoder_ws_bytes(int tokens, int hidden, int inter);
+/* hidden_out [B*L, hidden] f32 = last hidden state; ids [B,L] (any index dtype), mask [B,L] (attention mask:
+ * masked KEYS get softmax weight 0; masked query positions are still computed, as in the reference, and are
+ * ignored by the masked mean that follows).  err_flag (nullable) is set on an out-of-range token id. */
+int tt_encoder_fwd(const tt_encoder_weights* w, const void* ids, int ids_dtype, const void* mask, int mask_dtype,
+                   int B, int L, float* hidden_out, int* err_flag, void* ws, size_t ws_bytes, tt_stream_t stream);
+/* fp32 [rows, cols] dense -> bf16 terms hi = rn(x), lo = rn(x - hi). */
+int tt_split_bf16_terms(const float* x, int rows, int cols, void* hi, void* lo, tt_stream_t stream);
+
 /* Diagnostics / parity tests: device address of a named internal buffer of a tensor-core step workspace:
  * "trace" (task timeline of the persistent chain kernel after a TT_CHAIN_TRACE=1 step: [160][64] pairs of
  * {task << 2 | kind, globaltimer ns}), "h_hi" / "h_lo" / "dy_hi" / "dy_lo" (bf16 terms [3B,P], rows q | p | n). */

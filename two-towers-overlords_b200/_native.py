@@ -68,6 +68,17 @@ class StepArgs(ctypes.Structure):
     ]
 
 
+class EncoderLayer(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in ("wqkv_hi", "wqkv_lo", "bqkv", "wo_hi", "wo_lo", "bo", "ln1_g", "ln1_b", "w1_hi",
+                                        "w1_lo", "b1", "w2_hi", "w2_lo", "b2", "ln2_g", "ln2_b")]
+
+
+class EncoderWeights(ctypes.Structure):
+    _fields_ = [("word_emb", c_void_p), ("pos_emb", c_void_p), ("type_emb", c_void_p), ("emb_ln_g", c_void_p),
+                ("emb_ln_b", c_void_p), ("vocab", c_int), ("max_pos", c_int), ("hidden", c_int), ("heads", c_int),
+                ("inter", c_int), ("n_layers", c_int), ("ln_eps", c_float), ("layers", POINTER(EncoderLayer))]
+
+
 # name -> (restype, argtypes): exactly the symbols include/tt_b200.h declares
 _SIGNATURES = {
     "tt_version": (c_int, []),
@@ -114,6 +125,10 @@ _SIGNATURES = {
     "tt_assemble_triplets": (c_int, [POINTER(TokenBankDesc), POINTER(TokenBankDesc), c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, ctypes.c_uint64, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tt_encoder_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tt_encoder_fwd": (c_int, [POINTER(EncoderWeights), c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
+    "tt_split_bf16_terms": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tt_debug_step_buffer": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_char_p,
                                      POINTER(c_void_p)]),
     "tt_ubench_l2_read": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),

@@ -33,7 +33,7 @@ constexpr size_t gemm_smem(int stages) { return (size_t)stages * kStageBytes + 1
 
 struct alignas(64) GemmGroup {
   CUtensorMap a[3], b[3];  // bf16 terms of each operand: hi, lo (= fp32 - hi), lo2 (= fp32 - hi - lo)
-  int M, N, K, relu;
+  int M, N, K, relu;   // relu: 0 none, 1 ReLU, 2 GELU (erf)
   const float* bias;   // [N] nullable
   const float* gate;   // [M, ldc] nullable: result is zeroed where gate <= 0 (ReLU backward)
   float* C;            // [M, ldc] nullable
@@ -170,9 +170,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += __ldg(g.bias + n + j);
       }
-      if (g.relu) {
+      if (g.relu == 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (g.relu == 2) {  // exact (erf) GELU: the frozen encoder's intermediate activation
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
       }
       const size_t o = (size_t)m * g.ldc + n;
       if (g.gate && row_ok) {
@@ -779,6 +782,23 @@ int step_sm100(const StepSm100& s, cudaStream_t st) {
     if ((rc = launch_gemm(g, 2, np, 1, nullptr, 0, st))) return rc;
   }
   return 0;
+}
+
+// One contraction C = act(A B^T + bias) on the tensor cores for other parts of the library (the frozen encoder):
+// operands as bf16 (hi, lo) terms, K-major; outputs fp32 and / or bf16 terms (each nullable).
+int gemm_terms_sm100(const bf16* A_hi, const bf16* A_lo, long long lda, const bf16* B_hi, const bf16* B_lo, long long ldb,
+                     int M, int N, int K, const float* bias, int act, float* C, int ldc, bf16* C_hi, bf16* C_lo,
+                     cudaStream_t st) {
+  GemmDesc d{};
+  d.A = {A_hi, A_lo, lda};
+  d.B = {B_hi, B_lo, ldb};
+  d.M = M; d.N = N; d.K = K; d.bias = bias; d.relu = act;
+  d.C = C; d.ldc = ldc; d.C_hi = C_hi; d.C_lo = C_lo;
+  return launch_gemm(&d, 1, A_lo ? 3 : 1, 1, nullptr, 0, st);
+}
+
+int split_terms_sm100(const float* X, int R, int C, bf16* hi, bf16* lo, cudaStream_t st) {
+  return split_transpose(X, R, C, C, hi, lo, nullptr, nullptr, 0, 0, st);
 }
 
 }  // namespace tt

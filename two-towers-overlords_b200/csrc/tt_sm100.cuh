@@ -42,6 +42,12 @@ int step_sm100(const StepSm100& s, cudaStream_t st);
 bool chain_enabled();  // TT_CHAIN=0 selects the per-kernel chain
 int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st);
 
+// generic tensor-core contraction on bf16 (hi, lo) terms: C = act(A B^T + bias); act: 0 none, 1 ReLU, 2 GELU (erf)
+int gemm_terms_sm100(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, long long lda, const __nv_bfloat16* B_hi,
+                     const __nv_bfloat16* B_lo, long long ldb, int M, int N, int K, const float* bias, int act, float* C,
+                     int ldc, __nv_bfloat16* C_hi, __nv_bfloat16* C_lo, cudaStream_t st);
+int split_terms_sm100(const float* X, int R, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+
 size_t scan_sm100_ws_bytes(int Q, long long N, int P, int k);
 int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void* Db, int Q, long long N, int P, int k,
                     long long id_base, float* top_score, long long* top_id, void* ws, size_t ws_bytes, cudaStream_t st);

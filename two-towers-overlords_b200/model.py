@@ -25,8 +25,10 @@ from torch.nn import Linear, Module, Parameter, ReLU, Sequential
 
 try:
     from . import ops
+    from .encoder import MiniLMBackbone
 except ImportError:
     import ops
+    from encoder import MiniLMBackbone
 
 DEFAULT_MODEL = "sentence-transformers/all-MiniLM-L6-v2"
 VOCAB_SIZE = 30522
@@ -145,10 +147,21 @@ class AveragePoolingTower(Module):
         table_dtype: torch.dtype = torch.float32,
         train_table: bool = False,
         precision: Optional[str] = None,
+        backbone: str = "table",
     ):
         super().__init__()
         self.tokenizer = _load_tokenizer(model_name, vocab_size)
-        self.pretrained_model = TokenTableBackbone(vocab_size, hidden_size, table_dtype)
+        # "table": the north_star's backbone, E[input_ids].  "minilm": the reference's actual one, the
+        # frozen 6-layer MiniLM BertModel of model.py:24 (encoder.MiniLMBackbone, forward on the device)
+        if backbone not in ("table", "minilm"):
+            raise ValueError(f"backbone must be 'table' or 'minilm', got {backbone!r}")
+        self.backbone = backbone
+        if backbone == "minilm":
+            if train_table:
+                raise ValueError("the MiniLM backbone is frozen (model.py:28-30); train_table needs backbone='table'")
+            self.pretrained_model = MiniLMBackbone(vocab_size=vocab_size, hidden_size=hidden_size)
+        else:
+            self.pretrained_model = TokenTableBackbone(vocab_size, hidden_size, table_dtype)
         self.embedding_dim = self.pretrained_model.config.hidden_size
         # frozen backbone (model.py:28-30) unless the D2 extension is requested
         for param in self.pretrained_model.parameters():
@@ -176,6 +189,15 @@ class AveragePoolingTower(Module):
     def pooled(self, texts: TextsOrTokens) -> Tensor:
         """Normalised mean-pooled embeddings [B, hidden] (model.py:48-56)."""
         ids, mask = self.tokenize(texts)
+        if self.backbone == "minilm":
+            # model.py:51-56: last hidden state -> masked mean -> normalise.  The pool kernel gathers rows of a
+            # "table" by index: here the table is the hidden states and the index of token (b, l) is b * L + l.
+            if mask is None:
+                mask = torch.ones_like(ids)
+            hidden = self.pretrained_model(input_ids=ids, attention_mask=mask)[0]
+            B, L, H = hidden.shape
+            pos = torch.arange(B * L, device=hidden.device, dtype=torch.int64).view(B, L)
+            return ops.pool(hidden.view(B * L, H), pos, mask.to(hidden.device))
         return ops.pool(self.pretrained_model.table, ids, mask)
 
     def forward(self, texts: TextsOrTokens) -> Tensor:

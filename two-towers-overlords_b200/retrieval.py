@@ -38,17 +38,44 @@ class CorpusShard:
             self.Dn, self.Db = ops.l2_normalize_rows(doc_embeds), None
         else:
             self.Dn, self.Db = ops.l2_normalize_rows(doc_embeds, want_bf16=True)
+        self._graphs, self._seen = {}, {}
 
     def __len__(self):
         return self.Dn.shape[0]
 
-    def search(self, query_embeds: torch.Tensor, k: int = 10):
-        """-> (scores [Q,k], global ids [Q,k]) of this shard only."""
+    def _search_eager(self, query_embeds: torch.Tensor, k: int):
         if self.precision == "fp32":
             Qn, Qb = ops.l2_normalize_rows(query_embeds), None
         else:
             Qn, Qb = ops.l2_normalize_rows(query_embeds, want_bf16=True)
         return ops.scan_topk(Qn, self.Dn, k=k, id_base=self.id_base, precision=self.precision, Qb=Qb, Db=self.Db)
+
+    def search(self, query_embeds: torch.Tensor, k: int = 10, graph: bool = True):
+        """-> (scores [Q,k], global ids [Q,k]) of this shard only.
+
+        A search is six small launches (normalise, scan, refine, compaction, exact re-scan of unproven queries) plus
+        their host-side setup; on a small shard that fixed cost is longer than the scan itself (the latency path
+        `DocumentSearchEngine.search` serves).  A query shape seen twice is therefore captured into a CUDA graph —
+        one launch per search from then on; results are copies of the graph's static outputs."""
+        key = (tuple(query_embeds.shape), int(k), query_embeds.dtype)
+        if (not graph or len(self) == 0 or not 0 < query_embeds.shape[0] <= 1024  # big batches are scan-bound anyway
+                or torch.cuda.is_current_stream_capturing()):
+            return self._search_eager(query_embeds, k)
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if self._seen[key] < 2 or len(self._graphs) >= 8:
+                return self._search_eager(query_embeds, k)
+            q_static = query_embeds.detach().clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out_s, out_i = self._search_eager(q_static, k)
+            ent = self._graphs[key] = (g, q_static, out_s, out_i)
+        g, q_static, out_s, out_i = ent
+        q_static.copy_(query_embeds)
+        g.replay()
+        return out_s.clone(), out_i.clone()
 
 
 def all_gather_lists(top_s: torch.Tensor, top_i: torch.Tensor, world_size: int, group=None):
