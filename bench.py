@@ -456,6 +456,7 @@ def run_b200(args):
     del trainer, model
     torch.cuda.empty_cache()
     chain_variant = run_chain_variant(dev, args, ids_dtype, mask_dtype, host_packed) if (world == 1 and not args.no_chain_variant) else None
+    backbone_leg = run_backbone_leg(dev, args) if (world == 1 and not args.no_backbone) else None
     config2 = run_config2(dev, world, rank, args) if not args.no_config2 else None
     epoch_leg = run_epoch_leg(dev, world, rank, args) if not args.no_epoch else None
     torch.cuda.empty_cache()
@@ -474,7 +475,7 @@ def run_b200(args):
             "variant": {"projection_precision": args.precision, "table_dtype": args.table_dtype,
                         "dp_exchange": exchange_kind, "token_dtypes": f"ids {args.ids_dtype}, mask u8"},
             "graph_captures_in_timed_region": captures_in_timed, "dp_check": dp_check, "config2": config2,
-            "epoch_leg": epoch_leg, "projection_chain": chain_variant,
+            "epoch_leg": epoch_leg, "projection_chain": chain_variant, "full_backbone": backbone_leg,
             "dp_exchange_us": exchange_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
@@ -484,6 +485,77 @@ def run_b200(args):
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's actual backbone (frozen MiniLM-L6) in front of the same pool / projection / loss
+# --------------------------------------------------------------------------------------------------
+def run_backbone_leg(dev, args, B=256, steps=6):
+    """the reference-shaped training step (3 tower calls -> TripletLoss -> backward ->
+    torch.optim.Adam, backend/training.py:37-51) with `backbone="minilm"`: the frozen 6-layer encoder runs forward-only
+    on the device (tt_encoder_fwd), then the same masked-mean pool, projection and loss kernels.  Random-init weights
+    of the MiniLM-L6 shape, full-length tokens (32 / 256).  CPU beside it: transformers' BertModel forward for the same
+    token counts on a small sample (this is >99 % of the true reference's step)."""
+    from two_towers_overlords_b200 import TripletLoss, TwoTowersModel
+
+    torch.manual_seed(0)
+    model = TwoTowersModel(projection_dim=P_DIM, backbone="minilm", precision=args.precision).to(dev)
+    crit = TripletLoss(MARGIN)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR)
+    g = torch.Generator().manual_seed(11)
+
+    def toks(L):
+        return (torch.randint(999, VOCAB, (B, L), generator=g).to(dev), torch.ones(B, L, dtype=torch.int64, device=dev))
+
+    q, p, n = toks(LQ), toks(LD), toks(LD)
+
+    def step():
+        opt.zero_grad()
+        loss = crit(model.encode_queries(q), model.encode_documents(p), model.encode_documents(n))
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        loss = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    tokens = B * (LQ + 2 * LD)
+    # dense flops of the encoder per token: 6 layers x 2 x 384 x (3*384 + 384 + 1536 + 1536) + attention 4 x L x 384
+    enc_flops = sum(B * L * (6 * (2 * 384 * (4 * 384 + 2 * 1536) + 4 * L * 384)) for L in (LQ, LD, LD))
+    out = {"workload": f"training step with the frozen MiniLM-L6 backbone: {B} triplets, query {LQ} / doc {LD} tokens, "
+                       f"proj-dim {P_DIM}, Adam", "ms_per_step": ms, "triplets_per_s": B / (ms * 1e-3),
+           "tokens_per_s": tokens / (ms * 1e-3), "encoder_tflops": enc_flops / (ms * 1e-3) / 1e12,
+           "loss": float(loss.item())}
+    if not args.no_cpu:
+        try:
+            from transformers import BertConfig, BertModel
+
+            hf = BertModel(BertConfig(vocab_size=VOCAB, hidden_size=384, num_hidden_layers=6, num_attention_heads=12,
+                                      intermediate_size=1536)).eval()
+            bs = 8
+            ids = torch.randint(999, VOCAB, (bs, LD), generator=g)
+            with torch.no_grad():
+                hf(input_ids=ids)
+                t0 = time.time()
+                hf(input_ids=ids)
+                dt = time.time() - t0
+            cpu_tok_s = bs * LD / dt
+            out["cpu_baseline"] = {"tokens_per_s": cpu_tok_s, "triplets_per_s": cpu_tok_s / (LQ + 2 * LD),
+                                   "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": f"transformers BertModel forward, {bs} x {LD} tokens in {dt:.2f} s; a triplet is "
+                                             f"{LQ + 2 * LD} tokens (forward only: the backbone is frozen)"}
+        except Exception as ex:  # the leg is informative: a missing transformers install must not fail the bench
+            out["cpu_baseline"] = {"unavailable": repr(ex)}
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -917,6 +989,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-scan", action="store_true")
     ap.add_argument("--no-config2", action="store_true", help="skip the configs[2] leg (trainable tables, B=4096, P=384)")
+    ap.add_argument("--no-backbone", action="store_true", help="skip the frozen MiniLM-L6 backbone leg")
     ap.add_argument("--no-chain-variant", action="store_true", help="skip the projection-chain leg (persistent kernel vs one kernel per contraction)")
     ap.add_argument("--no-epoch", action="store_true", help="skip the configs[3] leg (~800k-triplet pass + NDCG@10)")
     ap.add_argument("--epoch-triplets", type=int, default=800_000)
