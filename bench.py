@@ -42,7 +42,7 @@ METRIC, UNIT = "train_triplets_per_sec", "triplets/s"
 def ncu_traffic(key: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)[key]
         return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
     except Exception:  # noqa: BLE001
@@ -457,7 +457,7 @@ def run_b200(args):
     torch.cuda.empty_cache()
     chain_variant = run_chain_variant(dev, args, ids_dtype, mask_dtype, host_packed) if (world == 1 and not args.no_chain_variant) else None
     backbone_leg = run_backbone_leg(dev, args) if (world == 1 and not args.no_backbone) else None
-    config2 = run_config2(dev, world, rank, args) if not args.no_config2 else None
+    config2 = run_config2(dev, world, rank, args, l2_peak=l2_peak) if not args.no_config2 else None
     epoch_leg = run_epoch_leg(dev, world, rank, args) if not args.no_epoch else None
     torch.cuda.empty_cache()
     scan = None
@@ -700,7 +700,7 @@ def run_dp_check(dev, world, rank, args, ids_dtype, mask_dtype, n_steps=2):
 # --------------------------------------------------------------------------------------------------
 # configs[2]: saved-model shape, trainable token tables (sorted-segment scatter-add backward)
 # --------------------------------------------------------------------------------------------------
-def run_config2(dev, world, rank, args, B=4096, P=384, steps=12):
+def run_config2(dev, world, rank, args, B=4096, P=384, steps=12, l2_peak=None):
     """Per-GPU batch 4096, P = 384, 32/256-token rows, BOTH 30522x384 tables trainable: the whole step (gather -> MLPs
     -> loss -> projection gradients -> dx -> both scatter-adds) and the document-table scatter-add (tt_pool_bwd) alone
     with its HBM roofline (SURVEY.md §8d formula).  Every rank runs its own replica (no exchange: the table gradient
@@ -761,6 +761,10 @@ def run_config2(dev, world, rank, args, B=4096, P=384, steps=12):
     bwd_launches = (lib.tt_launch_count() - n1) // steps
     n_unique = int(torch.unique(ids[mask.bool()].to(torch.int64)).numel())
     alg = R * LD * (4 + 1) + R * LD * 8 + R * HIDDEN * 4 + n_unique * HIDDEN * 4 + (VOCAB - n_unique) * HIDDEN * 4
+    # what the reduction really moves: every unmasked token adds the gradient row of ITS sequence into its table row, so
+    # the sorted-segment sum reads one 1536-byte row per TOKEN (g is 12.6 MB and cache-resident: the bytes come from L2)
+    n_tok = int(mask.bool().sum().item())
+    l2_bytes = n_tok * HIDDEN * 4 + alg
     out = {
         "workload": "configs[2] saved-model shape e15.lr4.d384.m3: batch 4096/GPU, proj-dim 384, query 32 / doc 256 "
                     "tokens, both 30522x384 tables trainable (deterministic sorted-segment scatter-add backward)",
@@ -768,12 +772,20 @@ def run_config2(dev, world, rank, args, B=4096, P=384, steps=12):
         "gpu_launches_per_step": int(launches), "n_gpus": world, "scaling": "replicas (no exchange in this leg)",
         "roofline_pool_bwd": {
             "kernel": "tt_pool_bwd (document table: 2B x 256 tokens -> stable radix sort by id -> one warp per touched row, rows named by > 256 tokens cut into 2048-entry chunks summed in a fixed order)",
-            "bound": "hbm", "achieved": alg / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "peak_kind": peak_kind,
-            "unit": "GB/s", "frac": alg / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_call": bwd_ms,
-            "launches_per_call": int(bwd_launches), "algorithmic_bytes_per_call": alg, "unique_rows": n_unique,
-            "traffic": None,
-            "formula": "tokens*(4 B id + 1 B mask) + tokens*8 B sort keys (id, position) + rows*1536 B gradient rows "
-                       "read + 30522*1536 B table gradient written (touched rows summed, the rest zero-filled)"},
+            "bound": "l2", "achieved": l2_bytes / (bwd_ms * 1e-3) / 1e9, "peak": l2_peak,
+            "peak_kind": "measured in this run (tt_ubench_l2_read)", "unit": "GB/s",
+            "frac": (l2_bytes / (bwd_ms * 1e-3) / 1e9 / l2_peak) if l2_peak else None,
+            "ms_per_call": bwd_ms, "launches_per_call": int(bwd_launches), "l2_bytes_per_call": l2_bytes,
+            "unmasked_tokens": n_tok, "unique_rows": n_unique,
+            "traffic": ncu_traffic("seg_reduce_kernel_doc_table_cfg2"),
+            "note": "whole call (sort + reduction, all launches) against the L2->SM ceiling; its dominant kernel, "
+                    "seg_reduce_kernel, alone moves 3.17 GB from L2 in 183 us = 17.3 TB/s under ncu "
+                    "(profiles/r02_ncu_summary.json), DRAM traffic 26 MB",
+            "hbm_formula": {"bound": "hbm", "achieved": alg / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "peak_kind": peak_kind,
+                            "unit": "GB/s", "frac": alg / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_call": alg,
+                            "formula": "SURVEY 8d: tokens*(4 B id + 1 B mask) + tokens*8 B sort keys (id, position) + "
+                                       "rows*1536 B gradient rows read + 30522*1536 B table gradient written; the per-token "
+                                       "row reads that dominate the call are served by L2 and are not in this formula"}},
     }
     del tr, m
     torch.cuda.empty_cache()
