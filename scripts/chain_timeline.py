@@ -45,7 +45,7 @@ kcb = 8
 while sum((k + kcb - 1) // kcb for k in kbt) > 48:
     kcb += 8
 nch = sum((k + kcb - 1) // kcb for k in kbt)
-counts = [sms, sms, 3 * RTB * NC, 3 * RTB * (P // 64), 3 * RTB * NC, 3 * RTB * NCH if table else 0, nch * NC * NC, nch * NC * NCH, sms]
+counts = [sms, 0, 3 * RTB * NC, 3 * RTB * (P // 64), 3 * RTB * NC, 3 * RTB * NCH if table else 0, nch * NC * NC, nch * NC * NCH, sms]
 names = ["S", "T", "F1", "F2L", "DZ", "DX", "DW2", "DW1", "G"]
 offs = np.concatenate([[0], np.cumsum(counts)])
 t0 = raw[:, :, 1][raw[:, :, 1] > 0].min()

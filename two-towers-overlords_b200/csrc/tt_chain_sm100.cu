@@ -6,16 +6,23 @@
 // (tt_gemm_sm100.cu: split -> fwd1 -> fwd2 -> loss -> dY^T -> dz1 -> dW2 -> colsums -> dW1 -> reduce) become
 // per-row-tile ready counters in global memory:
 //
-//   S    weights -> bf16 terms (+ transposes)                            SIMT, one task per CTA
-//   F1   h  = relu(x W1^T + b1)        -> h fp32, (hi,lo), transposed     tile (row tile, col tile)
+//   S    weights -> bf16 terms                                           SIMT, one task per CTA
+//   F1   h  = relu(x W1^T + b1)        -> (hi,lo) terms                   tile (row tile, col tile)
 //   F2L  y  = h W2^T + b2 for the q | p | n rows of 128 triplets (three accumulators), then in the SAME epilogue:
 //        partial |q|^2,|p|^2,|n|^2,q.p,q.n over this tile's columns -> exchanged with the sibling column tiles through
-//        global memory -> cosines, hinge, closed-form dY straight from TMEM -> dY (hi,lo), transposed, db2 partials
-//   DZ   dz1 = (dY W2) * (h > 0)       -> transposed (hi,lo), db1 partials [, (hi,lo) for DX]
+//        global memory -> cosines, hinge, closed-form dY straight from TMEM -> dY (hi,lo), db2 partials
+//   DZ   dz1 = (dY W2) * (h > 0)       -> (hi,lo), db1 partials
 //   DX   dxhat = dz1 W1                (only when the token tables train)
 //   DW2  dW2 partial = dY^T h  over a chunk of batch rows                 raw fp32 partial tile
 //   DW1  dW1 partial = dz1^T x over a chunk of batch rows
 //   G    gradients = fixed-order sums of the partials; loss; Adam step-count advance
+//
+// No transposed copy of anything exists: contractions whose reduction runs over the OUTER dimension of a row-major
+// operand (the weight gradients dW = dY^T h, dz1^T x reduce over batch rows; dz1 = dY W2 and dxhat = dz1 W1 reduce
+// over the weights' rows) read that operand as it lies in memory — TMA boxes of 64 k-rows x 64 elements, 128-byte
+// swizzle — and describe it to tcgen05.mma as MN-MAJOR (instruction-descriptor bits 15 / 16; shared-memory descriptor:
+// leading offset 8192 B between the two 64-element boxes of a 128-wide tile, stride offset 1024 B between groups of 8
+// k-rows, 2048 B per K = 16 step; checked bit-exact against the host by scripts/ubench/mn_major_test.cu).
 //
 // Warp roles per CTA: warp 0 = TMA producer (also waits for a task's dependencies), warp 1 = TMEM owner + single-thread
 // tcgen05.mma issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, 64 columns each).  The accumulators form
@@ -57,21 +64,20 @@ constexpr long long kSpinLimit = 4000000000ll;
 enum { T_S = 0, T_T, T_F1, T_F2L, T_DZ, T_DX, T_DW2, T_DW1, T_G, T_COUNT };
 
 struct TowerMaps {  // K-major bf16 operand terms of one tower (box 128 rows x 64 k)
-  CUtensorMap x[3], w1[3];   // F1:  [rows,H] x [P,H]
-  CUtensorMap h[2], w2[2];   // F2:  [rows,P] x [P,P]   (w2: boxes of 64 rows — the loss tiles are 64 columns wide)
-  CUtensorMap dy[2], w2t[2];  // DZ:  [rows,P] x [P,P]^T
-  CUtensorMap dyt[2], ht[2];  // DW2: [P,rows] x [P,rows]
-  CUtensorMap dzt[2], xt[2];  // DW1: [P,rows] x [H,rows]
-  CUtensorMap dz[2], w1t[2];  // DX:  [rows,P] x [H,P]
+  CUtensorMap x[3], w1[3];   // F1:  [rows,H] x [P,H]                          boxes of 128 rows x 64 k
+  CUtensorMap h[2], w2[2];   // F2:  [rows,P] x [P,P]   (w2: boxes of 64 rows — the loss tiles are 64 columns wide;
+                             //      DZ reads the same boxes as its MN-major B operand: 64 k-rows x 64 columns)
+  CUtensorMap dy[2];         // DZ:  A = dY [rows,P] K-major;  B = W2 [k][n] MN-major (w2 above)
+  CUtensorMap dz[2], w1k[2];  // DX:  A = dz1 [rows,P] K-major; B = W1 [k][n] MN-major
+  CUtensorMap dyk[2], hk[2];  // DW2: A = dY [k = batch row][m], B = h [k][n], both MN-major (boxes of 64 rows x 64)
+  CUtensorMap dzk[2], xk[2];  // DW1: A = dz1 [k][m], B = x [k][n], both MN-major
 };
 
-struct SplitJobC {  // fp32 [R, C] dense -> bf16 terms hi/lo[/lo2] [R, C] and (optional) transposed hi/lo [C, R]
+struct SplitJobC {  // fp32 [R, C] dense -> bf16 terms hi/lo[/lo2] [R, C]
   const float* X;
-  bf16 *hi, *lo, *lo2, *thi, *tlo;
+  bf16 *hi, *lo, *lo2;
   int R, C;
   int f4_0;    // first float4 of this matrix in the flat pass over all jobs
-  int t64_0;   // first 64 x 64 tile of this matrix in the transpose pass (-1: no transposed copy)
-  int tiles_c;
 };
 
 struct alignas(64) ChainParams {
@@ -80,17 +86,15 @@ struct alignas(64) ChainParams {
   int pairs, terms, pairs1, terms1;
   int kcb, nch[2], kbt[2];
   int off[T_COUNT + 1];
-  int stages, n_sj, n_split_f4, n_split_f4_w1, n_split_t64;
+  int stages, n_sj, n_split_f4, n_split_f4_w1;
   int nS;        // tasks of the S, T and G phases: one per CTA
   int krot;      // rotate the k-block order per CTA (tuning hook TT_CHAIN_KROT)
   int use_pdl;   // launched as a programmatic dependent of the pooled gather: wait for it before touching x
-  const bf16 *x_hi, *x_lo;
-  bf16 *xt_hi, *xt_lo;
   SplitJobC sj[6];
   float margin, inv_batch, grad_scale;
   const float *b1[2], *b2[2];
   float *h, *y, *dy, *dz1, *dxhat, *stats, *loss;
-  bf16 *h_hi, *h_lo, *ht_hi, *ht_lo, *dy_hi, *dy_lo, *dyt_hi, *dyt_lo, *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;
+  bf16 *h_hi, *h_lo, *dy_hi, *dy_lo, *dz_hi, *dz_lo;
   float *part2, *part1;
   float *dW1[2], *db1[2], *dW2[2], *db2[2];
   float *stat_part, *cs1, *cs2, *hinge_part, *ybuf;
@@ -163,6 +167,7 @@ struct Sub {
   const CUtensorMap *a, *b;
   int terms, pairs, m0, n0, kb0, nkb;
   int bn;  // MMA N = rows of the B box (128, or 64 for the loss tiles)
+  int amn, bmn;  // operand is MN-major: two boxes of 64 k-rows x 64 elements at (m0 | m0 + 64, k) instead of one K-major box
 };
 __device__ __forceinline__ int n_subs(int type) {
   return (type == T_S || type == T_T || type == T_G) ? 0 : 1;
@@ -179,6 +184,7 @@ __device__ __forceinline__ Sub get_sub(const ChainParams& p, Task tk, int k) {
   s.pairs = p.pairs;
   s.kb0 = 0;
   s.bn = BN;
+  s.amn = s.bmn = 0;
   switch (tk.type) {
     case T_F1: {
       const RowTile rt = row_tile(p, tk.i / p.NC);
@@ -194,19 +200,19 @@ __device__ __forceinline__ Sub get_sub(const ChainParams& p, Task tk, int k) {
     } break;
     case T_DZ: {
       const RowTile rt = row_tile(p, tk.i / p.NC);
-      s.a = p.tm[rt.t].dy; s.b = p.tm[rt.t].w2t;
+      s.a = p.tm[rt.t].dy; s.b = p.tm[rt.t].w2; s.bmn = 1;
       s.m0 = rt.trow; s.n0 = (tk.i % p.NC) * BN; s.nkb = p.P / BK;
     } break;
     case T_DX: {
       const RowTile rt = row_tile(p, tk.i / p.NCH);
-      s.a = p.tm[rt.t].dz; s.b = p.tm[rt.t].w1t;
+      s.a = p.tm[rt.t].dz; s.b = p.tm[rt.t].w1k; s.bmn = 1;
       s.m0 = rt.trow; s.n0 = (tk.i % p.NCH) * BN; s.nkb = p.P / BK;
     } break;
     case T_DW2: {
       const int nt_ = p.NC * p.NC, tile = tk.i % nt_;
       int t, j;
       dw_chunk(p, tk.i / nt_, t, j);
-      s.a = p.tm[t].dyt; s.b = p.tm[t].ht;
+      s.a = p.tm[t].dyk; s.b = p.tm[t].hk; s.amn = s.bmn = 1;
       s.m0 = (tile / p.NC) * BM; s.n0 = (tile % p.NC) * BN;
       s.kb0 = j * p.kcb; s.nkb = min(p.kcb, p.kbt[t] - s.kb0);
     } break;
@@ -214,7 +220,7 @@ __device__ __forceinline__ Sub get_sub(const ChainParams& p, Task tk, int k) {
       const int nt_ = p.NC * p.NCH, tile = tk.i % nt_;
       int t, j;
       dw_chunk(p, tk.i / nt_, t, j);
-      s.a = p.tm[t].dzt; s.b = p.tm[t].xt;
+      s.a = p.tm[t].dzk; s.b = p.tm[t].xk; s.amn = s.bmn = 1;
       s.m0 = (tile / p.NCH) * BM; s.n0 = (tile % p.NCH) * BN;
       s.kb0 = j * p.kcb; s.nkb = min(p.kcb, p.kbt[t] - s.kb0);
     } break;
@@ -263,12 +269,8 @@ __device__ __forceinline__ void wait_deps(const ChainParams& p, Task tk) {
       int t, j;
       dw_chunk(p, tk.i / nt_, t, j);
       const int k0 = j * p.kcb * BK, k1 = min(k0 + p.kcb * BK, t ? 2 * p.B : p.B);
-      if (tk.type == T_DW2) {
-        wait_rows(p, dy_ready(p), p.NCF, t, k0, k1);
-      } else {
-        wait_counter(p.ctr + 3, (unsigned)p.nS);  // transposed xhat terms
-        wait_rows(p, dz_ready(p), p.NC, t, k0, k1);
-      }
+      if (tk.type == T_DW2) wait_rows(p, dy_ready(p), p.NCF, t, k0, k1);
+      else wait_rows(p, dz_ready(p), p.NC, t, k0, k1);
     } break;
     default: break;
   }
@@ -309,15 +311,6 @@ __device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
 __device__ __forceinline__ void split16(const float (&v)[16], bf16 (&hi)[16], bf16 (&lo)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) split_bf16(v[j], hi[j], lo[j]);
-}
-// transposed copy [n + j][tcol]: lanes hold consecutive rows, so each store instruction is one 64 B run per column
-__device__ __forceinline__ void store_t(const bf16 (&hi)[16], const bf16 (&lo)[16], bf16* t_hi, bf16* t_lo, int n, int ldt,
-                                        int tcol) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    t_hi[(size_t)(n + j) * ldt + tcol] = hi[j];
-    t_lo[(size_t)(n + j) * ldt + tcol] = lo[j];
-  }
 }
 // this lane's 16 bf16 (32 B) -> row `lane` of a staged block
 __device__ __forceinline__ void stage16(uint8_t* blk, int lane, const bf16 (&x)[16]) {
@@ -411,8 +404,7 @@ __device__ __forceinline__ uint32_t pack_bf16(bf16 a, bf16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// weights of both towers -> bf16 terms: (a) one flat float4 pass over all matrices for the row-major terms, every
-// load of a thread in flight at once; (b) 64 x 64 tiles through shared memory for the transposed copies
+// weights of both towers -> bf16 terms: one flat float4 pass over all matrices, every load of a thread in flight at once
 __device__ void epi_split(const ChainParams& p, EpiCtx& e, int task_i) {
   const int nS = p.nS;
   if (task_i == 0 && e.tid == 0 && p.adam_state) {
@@ -468,92 +460,8 @@ __device__ void epi_split(const ChainParams& p, EpiCtx& e, int task_i) {
       if (e.tid == 0) signal(p.ctr + 0);
     }
   }
-  // (b) transposed copies
-  bf16* s_hi = e.sp_s;
-  bf16* s_lo = e.sp_s + 64 * kSplitPad;
-  for (int tile = task_i; tile < p.n_split_t64; tile += nS) {
-    int j = -1;
-    for (int k = 0; k < p.n_sj; ++k)
-      if (p.sj[k].t64_0 >= 0 && tile >= p.sj[k].t64_0) j = k;
-    const SplitJobC& J = p.sj[j];
-    const int lt = tile - J.t64_0;
-    const int r0 = (lt / J.tiles_c) * 64, c0 = (lt % J.tiles_c) * 64;
-    float4 v[4];
-    const int rr = e.tid >> 4, c4 = e.tid & 15;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      v[i] = __ldg(reinterpret_cast<const float4*>(J.X + (size_t)(r0 + rr + 16 * i) * J.C + c0) + c4);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        bf16 h, l;
-        split_bf16(x[k], h, l);
-        s_hi[(c4 * 4 + k) * kSplitPad + rr + 16 * i] = h;
-        s_lo[(c4 * 4 + k) * kSplitPad + rr + 16 * i] = l;
-      }
-    }
-    epi_bar();
-    // transposed tile: row c (64 of them) holds 64 consecutive r; a thread moves bf16 pairs, a warp one 128 B run
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int item = e.tid + i * kEpiThreads;  // 64 rows x 32 pairs
-      const int cc = item >> 5, rp = item & 31;
-      const uint32_t a = *reinterpret_cast<const uint32_t*>(s_hi + cc * kSplitPad + 2 * rp);
-      const uint32_t b = *reinterpret_cast<const uint32_t*>(s_lo + cc * kSplitPad + 2 * rp);
-      const size_t o = (size_t)(c0 + cc) * J.R + r0 + 2 * rp;
-      *reinterpret_cast<uint32_t*>(J.thi + o) = a;
-      *reinterpret_cast<uint32_t*>(J.tlo + o) = b;
-    }
-    epi_bar();
-  }
   publish(e);
   if (e.tid == 0) signal(p.ctr + 2);
-}
-
-// xhat terms [3B, H] -> transposed [H, ldt] (query rows at columns [0, B), document rows from column dcol on): the
-// K-major operand of the first layer's weight gradient.  64 x 64 tiles through shared memory.
-__device__ void epi_transpose_x(const ChainParams& p, EpiCtx& e, int task_i) {
-  bf16* s_t[2] = {e.sp_s, e.sp_s + 64 * kSplitPad};
-  const bf16* src[2] = {p.x_hi, p.x_lo};
-  bf16* dst[2] = {p.xt_hi, p.xt_lo};
-  const int R = 3 * p.B, tiles_c = p.H / 64, ntiles = ((R + 63) / 64) * tiles_c;
-  for (int tile = task_i; tile < ntiles; tile += p.nS) {
-    const int r0 = (tile / tiles_c) * 64, c0 = (tile % tiles_c) * 64;
-    uint4 v[2][2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int item = e.tid + i * kEpiThreads, rr = item >> 3, sg = item & 7;  // 64 rows x 8 segments of 16 B
-        v[t][i] = (r0 + rr < R) ? __ldcg(reinterpret_cast<const uint4*>(src[t] + (size_t)(r0 + rr) * p.H + c0) + sg)
-                                : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int item = e.tid + i * kEpiThreads, rr = item >> 3, sg = item & 7;
-        const bf16* x = reinterpret_cast<const bf16*>(&v[t][i]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s_t[t][(sg * 8 + k) * kSplitPad + rr] = x[k];
-      }
-    epi_bar();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int item = e.tid + i * kEpiThreads;  // 64 transposed rows x 64 elements
-      const int cc = item >> 6, rr = item & 63, g = r0 + rr;
-      if (g < R) {
-        const size_t o = (size_t)(c0 + cc) * p.ldt + (g < p.B ? g : p.dcol + (g - p.B));
-        dst[0][o] = s_t[0][cc * kSplitPad + rr];
-        dst[1][o] = s_t[1][cc * kSplitPad + rr];
-      }
-    }
-    epi_bar();
-  }
-  publish(e);
-  if (e.tid == 0) signal(p.ctr + 3);
 }
 
 __device__ __forceinline__ int warp_valid_rows(const EpiCtx& e, int valid) { return max(0, min(32, valid - e.q * 32)); }
@@ -568,7 +476,6 @@ __device__ void epi_f1(const ChainParams& p, EpiCtx& e, int task_i) {
   const bool ok = row < rt.valid;
   const int vr = warp_valid_rows(e, rt.valid);
   const size_t wrow0 = (size_t)rt.grow + e.q * 32;
-  const int tcol = (rt.t ? p.dcol : 0) + rt.trow + row;
   const float* bias = p.b1[rt.t];
   for (int ch = 0; ch < 4; ++ch) {
     const int n = n0 + e.hf * 64 + ch * 16;
@@ -581,10 +488,7 @@ __device__ void epi_f1(const ChainParams& p, EpiCtx& e, int task_i) {
     split16(v, hi, lo);
     stage16(e.rs, e.lane, hi);
     stage16(e.rs + kTermBlock, e.lane, lo);
-    if (ok) {
-      store_t(hi, lo, p.ht_hi, p.ht_lo, n, p.ldt, tcol);
-      if (p.h) store16(p.h + (wrow0 + e.lane) * p.P + n, v);
-    }
+    if (ok && p.h) store16(p.h + (wrow0 + e.lane) * p.P + n, v);
     __syncwarp();
     flush16(e.rs, e.lane, p.h_hi, wrow0, n, p.P, vr);
     flush16(e.rs + kTermBlock, e.lane, p.h_lo, wrow0, n, p.P, vr);
@@ -710,7 +614,6 @@ __device__ void epi_f2l(const ChainParams& p, EpiCtx& e, int task_i) {
     const float hsum = warp_sum(hinge);
     if (e.lane == 0) e.hs_s[e.q] = hsum;
   }
-  const int tcol = seg == 0 ? trip : p.dcol + (seg - 1) * p.B + trip;
   uint8_t* blk_hi = e.rs;
   uint8_t* blk_lo = e.rs + kTermBlock;
 #pragma unroll
@@ -724,10 +627,7 @@ __device__ void epi_f2l(const ChainParams& p, EpiCtx& e, int task_i) {
     split16(g, hi, lo);
     stage16(blk_hi, e.lane, hi);
     stage16(blk_lo, e.lane, lo);
-    if (ok) {
-      store_t(hi, lo, p.dyt_hi, p.dyt_lo, n, p.ldt, tcol);
-      if (p.dy) store16(p.dy + ((size_t)seg * p.B + trip) * p.P + n, g);
-    }
+    if (ok && p.dy) store16(p.dy + ((size_t)seg * p.B + trip) * p.P + n, g);
     __syncwarp();
     flush16(blk_hi, e.lane, p.dy_hi, wrow0, n, p.P, vr);
     flush16(blk_lo, e.lane, p.dy_lo, wrow0, n, p.P, vr);
@@ -754,7 +654,6 @@ __device__ void epi_dz(const ChainParams& p, EpiCtx& e, int task_i) {
   const bool ok = row < rt.valid;
   const int vr = warp_valid_rows(e, rt.valid);
   const size_t wrow0 = (size_t)rt.grow + e.q * 32;
-  const int tcol = (rt.t ? p.dcol : 0) + rt.trow + row;
   for (int ch = 0; ch < 4; ++ch) {
     const int n = n0 + e.hf * 64 + ch * 16;
     if (n >= p.P) break;
@@ -775,15 +674,12 @@ __device__ void epi_dz(const ChainParams& p, EpiCtx& e, int task_i) {
     }
     alignas(16) bf16 hi[16], lo[16];
     split16(v, hi, lo);
-    if (ok) store_t(hi, lo, p.dzt_hi, p.dzt_lo, n, p.ldt, tcol);
-    if (p.dz_hi) {
-      stage16(e.rs, e.lane, hi);
-      stage16(e.rs + kTermBlock, e.lane, lo);
-      __syncwarp();
-      flush16(e.rs, e.lane, p.dz_hi, wrow0, n, p.P, vr);
-      flush16(e.rs + kTermBlock, e.lane, p.dz_lo, wrow0, n, p.P, vr);
-      __syncwarp();
-    }
+    stage16(e.rs, e.lane, hi);  // (rows past the batch are zero: the weight-gradient contraction reads whole k-blocks)
+    stage16(e.rs + kTermBlock, e.lane, lo);
+    __syncwarp();
+    flush16(e.rs, e.lane, p.dz_hi, wrow0, n, p.P, vr);
+    flush16(e.rs + kTermBlock, e.lane, p.dz_lo, wrow0, n, p.P, vr);
+    __syncwarp();
     stage_cs(e, 0, ch, colsum16(v, e.lane));
   }
   tc_fence_before();
@@ -1035,8 +931,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             for (int j = 0; j < sb.terms; ++j) {
               mbar_wait(&empty[s], ph ^ 1u);
               mbar_arrive_expect_tx(&full[s], kABytes + (uint32_t)sb.bn * BK * 2);
-              tma_load_2d(smem + s * kStageBytes, &sb.a[j], &full[s], kb * BK, sb.m0);
-              tma_load_2d(smem + s * kStageBytes + kABytes, &sb.b[j], &full[s], kb * BK, sb.n0);
+              uint8_t* sa = smem + s * kStageBytes;
+              uint8_t* sbm = sa + kABytes;
+              if (sb.amn) {  // MN-major: [64 k-rows][64 m] boxes for m0 .. m0+63 and m0+64 .. m0+127
+                tma_load_2d(sa, &sb.a[j], &full[s], sb.m0, kb * BK);
+                tma_load_2d(sa + kABytes / 2, &sb.a[j], &full[s], sb.m0 + 64, kb * BK);
+              } else {
+                tma_load_2d(sa, &sb.a[j], &full[s], kb * BK, sb.m0);
+              }
+              if (sb.bmn) {
+                tma_load_2d(sbm, &sb.b[j], &full[s], sb.n0, kb * BK);
+                tma_load_2d(sbm + kBBytes / 2, &sb.b[j], &full[s], sb.n0 + 64, kb * BK);
+              } else {
+                tma_load_2d(sbm, &sb.b[j], &full[s], kb * BK, sb.n0);
+              }
               if (++s == NS) {
                 s = 0;
                 ph ^= 1u;
@@ -1057,7 +965,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         const int ns = n_subs(tk.type);
         for (int k = 0; k < ns; ++k) {
           const Sub sb = get_sub(p, tk, k);
-          const uint32_t idesc = sb.bn == BN ? idesc128 : idesc64;
+          // MN-major operands: instruction-descriptor bits 15 (A) / 16 (B)
+          const uint32_t idesc = (sb.bn == BN ? idesc128 : idesc64) | ((uint32_t)sb.amn << 15) | ((uint32_t)sb.bmn << 16);
+          // per K = 16 step a K-major operand advances 32 B inside its 128-byte rows, an MN-major one two groups of
+          // 8 k-rows (2 x 1024 B); descriptor units are 16 B
+          const uint64_t a_step = sb.amn ? 128 : 2, b_step = sb.bmn ? 128 : 2;
           mbar_wait(&acc_empty[ab], aph ^ 1u);
           tc_fence_after();
           const uint32_t acc = tmem_base + (uint32_t)(ab * BN);
@@ -1076,11 +988,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             tc_fence_after();
             for (int pair = 0; pair < sb.pairs; ++pair) {
               const int ai = (0x201100 >> (4 * pair)) & 3, bi = (0x021010 >> (4 * pair)) & 3;
-              const uint64_t da = make_smem_desc_sw128(slot_addr[ai]),
-                             db = make_smem_desc_sw128(slot_addr[bi] + kABytes);
+              const uint64_t da = sb.amn ? make_smem_desc_sw128_mn(slot_addr[ai], kABytes / 2) : make_smem_desc_sw128(slot_addr[ai]),
+                             db = sb.bmn ? make_smem_desc_sw128_mn(slot_addr[bi] + kABytes, kBBytes / 2)
+                                         : make_smem_desc_sw128(slot_addr[bi] + kABytes);
 #pragma unroll
               for (int kk = 0; kk < BK / 16; ++kk)
-                mma_bf16(acc, da + 2 * kk, db + 2 * kk, idesc, (kbi | pair | kk) != 0);
+                mma_bf16(acc, da + a_step * kk, db + b_step * kk, idesc, (kbi | pair | kk) != 0);
             }
             for (int j = 0; j < sb.terms; ++j) mma_commit(&empty[slot_id[j]]);
           }
@@ -1119,7 +1032,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
           epi_split(p, e, tk.i);
           if (p.use_pdl) pdl_wait();  // the pooled gather's xhat terms are read from here on
           break;
-        case T_T: epi_transpose_x(p, e, tk.i); break;
         case T_F1: epi_f1(p, e, tk.i); break;
         case T_F2L: epi_f2l(p, e, tk.i); break;
         case T_DZ: epi_dz(p, e, tk.i); break;
@@ -1186,7 +1098,7 @@ int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st) {
   int rc;
   const float* W1[2] = {s.Wq1, s.Wd1};
   const float* W2[2] = {s.Wq2, s.Wd2};
-  const int row0[2] = {0, B}, rows[2] = {B, 2 * B}, tcol[2] = {0, w.dcol};
+  const int row0[2] = {0, B}, rows[2] = {B, 2 * B};
   const bool x3 = s.n_split == 3;
   for (int t = 0; t < 2; ++t) {
     TowerMaps& m = p.tm[t];
@@ -1196,29 +1108,23 @@ int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st) {
     const bf16* hh[2] = {w.h_hi + oP, w.h_lo + oP};
     const bf16* w2[2] = {w.w2_hi[t], w.w2_lo[t]};
     const bf16* dy[2] = {w.dy_hi + oP, w.dy_lo + oP};
-    const bf16* w2t[2] = {w.w2t_hi[t], w.w2t_lo[t]};
-    const bf16* dyt[2] = {w.dyt_hi + tcol[t], w.dyt_lo + tcol[t]};
-    const bf16* ht[2] = {w.ht_hi + tcol[t], w.ht_lo + tcol[t]};
-    const bf16* dzt[2] = {w.dzt_hi + tcol[t], w.dzt_lo + tcol[t]};
-    const bf16* xt[2] = {w.xt_hi + tcol[t], w.xt_lo + tcol[t]};
     const bf16* dz[2] = {w.dz_hi + oP, w.dz_lo + oP};
-    const bf16* w1t[2] = {w.w1t_hi[t], w.w1t_lo[t]};
     if ((rc = map_terms(m.x, 3, x, rows[t], H, H))) return rc;
     if ((rc = map_terms(m.w1, 3, w1, P, H, H))) return rc;
     if ((rc = map_terms(m.h, 2, hh, rows[t], P, P))) return rc;
     if ((rc = map_terms(m.w2, 2, w2, P, P, P, 64))) return rc;
     if ((rc = map_terms(m.dy, 2, dy, rows[t], P, P))) return rc;
-    if ((rc = map_terms(m.w2t, 2, w2t, P, P, P))) return rc;
-    if ((rc = map_terms(m.dyt, 2, dyt, P, rows[t], w.ldt))) return rc;
-    if ((rc = map_terms(m.ht, 2, ht, P, rows[t], w.ldt))) return rc;
-    if ((rc = map_terms(m.dzt, 2, dzt, P, rows[t], w.ldt))) return rc;
-    if ((rc = map_terms(m.xt, 2, xt, H, rows[t], w.ldt))) return rc;
     if ((rc = map_terms(m.dz, 2, dz, rows[t], P, P))) return rc;
-    if ((rc = map_terms(m.w1t, 2, w1t, H, P, P))) return rc;
+    // MN-major operands: the same row-major arrays, boxes of 64 k-rows x 64 elements
+    if ((rc = map_terms(m.w1k, 2, w1, P, H, H, 64))) return rc;
+    if ((rc = map_terms(m.dyk, 2, dy, rows[t], P, P, 64))) return rc;
+    if ((rc = map_terms(m.hk, 2, hh, rows[t], P, P, 64))) return rc;
+    if ((rc = map_terms(m.dzk, 2, dz, rows[t], P, P, 64))) return rc;
+    if ((rc = map_terms(m.xk, 2, x, rows[t], H, H, 64))) return rc;
   }
   p.B = B; p.H = H; p.P = P;
   p.RTB = (B + BM - 1) / BM; p.NC = (P + BN - 1) / BN; p.NCH = (H + BN - 1) / BN; p.NCF = P / 64;
-  p.ldt = w.ldt; p.dcol = w.dcol;
+  p.ldt = w.ldt; p.dcol = w.dcol;  // (unused by the kernel now; kept in the parameter block for the trace tools)
   p.pairs = x3 ? 3 : 1; p.terms = x3 ? 2 : 1;
   {
     const char* e = getenv("TT_FWD1_PRODUCTS");  // tuning hook shared with the per-kernel chain
@@ -1240,7 +1146,7 @@ int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st) {
              3 * (P / 64), grid);
   const int n_rt = 3 * p.RTB, nchs = p.nch[0] + p.nch[1];
   const int count[T_COUNT] = {grid,
-                              grid,
+                              0,  // (T: the xhat transposition of earlier builds; no transposed copy exists any more)
                               n_rt * p.NC,
                               n_rt * p.NCF,
                               n_rt * p.NC,
@@ -1254,33 +1160,26 @@ int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st) {
   p.stages = chain_stages();
   // weights of both towers -> bf16 terms (+ transposes for the backward contractions); the first-layer weights come
   // first in the flat pass: layer 1 starts as soon as THEY are split (counter 0), the rest signals counter 2
-  int f4 = 0, t64 = 0;
+  int f4 = 0;
   p.n_sj = 0;
   for (int t = 0; t < 2; ++t) {
-    SplitJobC a{W1[t], w.w1_hi[t], w.w1_lo[t], x3 ? w.w1_lo2[t] : nullptr, s.dxhat ? w.w1t_hi[t] : nullptr,
-                s.dxhat ? w.w1t_lo[t] : nullptr, P, H, f4, s.dxhat ? t64 : -1, H / 64};
+    p.sj[p.n_sj++] = SplitJobC{W1[t], w.w1_hi[t], w.w1_lo[t], x3 ? w.w1_lo2[t] : nullptr, P, H, f4};
     f4 += P * H / 4;
-    if (s.dxhat) t64 += (P / 64) * (H / 64);
-    p.sj[p.n_sj++] = a;
   }
   p.n_split_f4_w1 = f4;
   for (int t = 0; t < 2; ++t) {
-    SplitJobC b{W2[t], w.w2_hi[t], w.w2_lo[t], nullptr, w.w2t_hi[t], w.w2t_lo[t], P, P, f4, t64, P / 64};
+    p.sj[p.n_sj++] = SplitJobC{W2[t], w.w2_hi[t], w.w2_lo[t], nullptr, P, P, f4};
     f4 += P * P / 4;
-    t64 += (P / 64) * (P / 64);
-    p.sj[p.n_sj++] = b;
   }
   p.n_split_f4 = f4;
-  p.n_split_t64 = t64;
   p.margin = s.margin; p.inv_batch = s.inv_batch; p.grad_scale = s.grad_scale;
   p.b1[0] = s.bq1; p.b1[1] = s.bd1; p.b2[0] = s.bq2; p.b2[1] = s.bd2;
   const bool dbg = chain_debug_out() != 0;
   p.h = dbg ? s.h : nullptr; p.y = dbg ? s.y : nullptr; p.dy = dbg ? s.dy : nullptr; p.dz1 = dbg ? w.dz1 : nullptr;
   p.dxhat = s.dxhat; p.stats = s.stats; p.loss = s.loss;
-  p.h_hi = w.h_hi; p.h_lo = w.h_lo; p.ht_hi = w.ht_hi; p.ht_lo = w.ht_lo;
-  p.dy_hi = w.dy_hi; p.dy_lo = w.dy_lo; p.dyt_hi = w.dyt_hi; p.dyt_lo = w.dyt_lo;
-  p.dz_hi = s.dxhat ? w.dz_hi : nullptr; p.dz_lo = s.dxhat ? w.dz_lo : nullptr;
-  p.dzt_hi = w.dzt_hi; p.dzt_lo = w.dzt_lo;
+  p.h_hi = w.h_hi; p.h_lo = w.h_lo;
+  p.dy_hi = w.dy_hi; p.dy_lo = w.dy_lo;
+  p.dz_hi = w.dz_hi; p.dz_lo = w.dz_lo;
   p.part2 = w.partial2; p.part1 = w.partial;
   p.dW1[0] = s.dWq1; p.dW1[1] = s.dWd1; p.db1[0] = s.dbq1; p.db1[1] = s.dbd1;
   p.dW2[0] = s.dWq2; p.dW2[1] = s.dWd2; p.db2[0] = s.dbq2; p.db2[1] = s.dbd2;
@@ -1292,7 +1191,6 @@ int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st) {
     const char* e = getenv("TT_CHAIN_KROT");
     p.krot = e ? atoi(e) : 0;  // off: no speed-up measured, and ascending k keeps the rounding correlated with the fp32 oracle
   }
-  p.x_hi = w.x_hi; p.x_lo = w.x_lo; p.xt_hi = w.xt_hi; p.xt_lo = w.xt_lo;
   if (s.adam.param) {
     const FusedAdam& a = s.adam;
     TT_REQUIRE(a.state && a.grad && a.exp_avg && a.exp_avg_sq, "tt_triplet_step: fused Adam needs state, grad and both moments");

@@ -245,7 +245,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::f16 instruction descriptor: BF16 x BF16 -> F32, both operands K-major, M x N tile
+// MN-major operand, 128-byte swizzle: the tile is a row of [64 k-rows x 64 elements] boxes (one per 64 elements of the
+// M / N extent, `box_bytes` apart = leading offset); inside a box, groups of 8 k-rows are 1024 B apart (stride offset).
+// A K = 16 step advances the start address by two such groups (2048 B).  Verified by scripts/ubench/mn_major_test.cu.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t box_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((box_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: BF16 x BF16 -> F32, both operands K-major (OR in bit 15 / 16 for an MN-major A / B),
+// M x N tile
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
