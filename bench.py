@@ -431,8 +431,8 @@ def run_b200(args):
         "algorithmic_bytes_per_launch": alg_bytes_per_triplet * B_PER_GPU, "us_per_launch": pool_ms * 1e3,
         "share_of_step": pool_ms / (ms_total / K),
         "share_of_serialised_step": pool_ms / seq_ms, "serialised_step_ms": seq_ms,
-        "share_note": "timed alone; inside a step this kernel (for step i+1) runs BESIDE the tensor-core chain of "
-                      "step i, so the shares of the two do not add up to 1; share_of_serialised_step divides by the "
+        "share_note": "timed alone (tables cache-warm); with the per-kernel chain (TT_CHAIN=0) or under data "
+                      "parallelism this kernel (for step i+1) runs BESIDE other work of step i; share_of_serialised_step divides by the "
                       "step time with nothing overlapped and is the figure to compare with the ncu launch list",
     }
 
@@ -623,10 +623,9 @@ def run_chain_variant(dev, args, ids_dtype, mask_dtype, host_packed, steps=40):
             os.environ.pop("TT_CHAIN", None)
         else:
             os.environ["TT_CHAIN"] = prev
-    out["note"] = ("the persistent kernel is the shorter chain but holds every SM (one 320-thread CTA with ~210 KB of "
-                   "shared memory each), so the look-ahead gather cannot run beside it; FusedTrainer therefore keeps "
-                   "one kernel per contraction when there is a look-ahead gather to overlap and uses the persistent "
-                   "kernel for whole-step calls (trainable tables)")
+    out["note"] = ("the persistent kernel holds every SM (one 320-thread CTA with ~190 KB of shared memory each), so a "
+                   "step is gather -> chain (2 launches); the per-kernel chain lets the NEXT step's gather run beside "
+                   "its 17 small kernels.  FusedTrainer's default is the persistent kernel (TT_CHAIN=0 selects the other)")
     return out
 
 

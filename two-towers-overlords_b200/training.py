@@ -212,17 +212,19 @@ class FusedTrainer:
                                 torch.zeros_like(dt.pretrained_model.table, dtype=torch.float32))
         # TWO step workspaces: the pooled gather of step i+1 (tokens + frozen tables only, never the projection
         # weights) runs beside everything else of step i, so consecutive steps alternate between them
-        # How the projection chain is launched (tt_step_args.chain).  The persistent kernel is the shorter chain
-        # (135 vs 171 us alone at configs[1], 2 launches per step instead of 18) but wants every SM, so nothing runs
-        # beside it; the per-kernel chain lets the look-ahead gather of the next step slip between its small kernels,
-        # and that overlap is worth more: measured on B200 0.249 vs 0.258 ms/step on one GPU, 0.274 vs 0.291 at N = 2.
-        # A trainable table has no look-ahead (the gather reads the table the step updates): persistent there.
-        # TT_CHAIN=1 / 0 forces either.
+        # How the projection chain is launched (tt_step_args.chain).  Default: the persistent chain kernel — everything
+        # after the pooled gather in ONE launch (129 us alone at configs[1] against 157 us for one kernel per
+        # contraction).  It wants every SM, so nothing runs beside it: on one GPU a step is gather -> chain in one stream
+        # (2 launches, the second a programmatic dependent of the first; 0.2466 ms), under data parallelism the NEXT
+        # step's gather runs beside the exchange kernel, which mostly waits (N = 2: 0.272 ms).  The per-kernel chain
+        # (TT_CHAIN=0) lets the look-ahead gather's CTAs slip between its small kernels instead; since the chain kernel
+        # lost its transposed copies that schedule is the slower one (0.2480 ms; N = 2: 0.275 ms).  A trainable table
+        # has no look-ahead in either mode (the gather reads the table the step updates).
         env_chain = os.environ.get("TT_CHAIN")
         if env_chain is not None:
             self.chain_mode = 1 if env_chain != "0" else 2
         else:
-            self.chain_mode = 1 if self.train_table else 2
+            self.chain_mode = 1
         self.step_objs = []
         for _ in range(2):
             so = ops.TripletStep(batch_size, Lq, Ld, self.H, self.P, self.vocab, self.precision, dev,
