@@ -24,12 +24,12 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
-# pick the 5th pool kernel as the start of a steady-state step
-pools = [i for i, e in enumerate(evs) if "pool_fwd" in e.name]
-adams = [i for i, e in enumerate(evs) if "adam_dev" in e.name]
-a0, a1 = adams[3], adams[4]
+# steady state: from the end of the 4th step-closing kernel (Adam launch, or the chain kernel that carries Adam) to the
+# end of the 5th
+closers = [i for i, e in enumerate(evs) if "adam_dev" in e.name] or [i for i, e in enumerate(evs) if "chain_kernel" in e.name]
+a0, a1 = closers[3], closers[4]
 t0 = evs[a0].time_range.end
-print(f"step = [end of adam #3, end of adam #4] = {evs[a1].time_range.end - t0:.1f} us")
+print(f"step = [end of step-closing kernel #3, end of #4] = {evs[a1].time_range.end - t0:.1f} us")
 for e in evs[a0 + 1: a1 + 1]:
     name = e.name.split("(")[0].split("::")[-1][:34]
     print(f"{e.time_range.start - t0:8.1f} +{e.time_range.end - e.time_range.start:7.1f} us  {name}")

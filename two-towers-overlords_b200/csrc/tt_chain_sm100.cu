@@ -104,7 +104,7 @@ struct alignas(64) ChainParams {
   double* adam_state;  // {t, beta1^t, beta2^t, -}: advanced once per launch (by the first task), read by the tail
   float *adam_p, *adam_g, *adam_m, *adam_v;
   float lr, beta1, beta2, eps;
-  unsigned total_signals;
+  unsigned total_signals, dw2_signals;
   unsigned long long* trace;  // nullable (TT_CHAIN_TRACE=1)
 };
 
@@ -738,7 +738,10 @@ __device__ void epi_dw(const ChainParams& p, EpiCtx& e, Task tk) {
   acc_advance(e, 1);
   __threadfence();
   epi_bar();
-  if (e.tid == 0) signal(p.ctr + 1);
+  if (e.tid == 0) {
+    if (two) signal(p.ctr + 5);  // the second-layer gradient's partial tiles: the tail sums them without waiting for dW1
+    signal(p.ctr + 1);
+  }
 }
 
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -783,7 +786,9 @@ __device__ __forceinline__ void emit1(const ChainParams& p, const AdamCoef& k, f
 // Nothing else reads the fp32 parameters any more at this point (the weights were split into bf16 terms by S, the
 // biases were last read by the F1 / F2L epilogues, all of which have signalled), so they are updated in place.
 __device__ void epi_grad(const ChainParams& p, EpiCtx& e, int task_i) {
-  if (e.tid == 0) wait_counter(p.ctr + 1, p.total_signals);
+  // phase A needs the dW2 partial tiles only: CTAs that run out of contraction tasks start here while others still work
+  // on dW1 (W2's fp32 values were last read by S, so its Adam update is safe already)
+  if (e.tid == 0) wait_counter(p.ctr + 5, p.dw2_signals);
   epi_bar();
   trace_ev(e, 2);
   AdamCoef k{0.f, 1.f};
@@ -793,52 +798,60 @@ __device__ void epi_grad(const ChainParams& p, EpiCtx& e, int task_i) {
     k.bc2_sqrt = (float)sqrt(1.0 - st[2]);
   }
   const int nG = p.off[T_COUNT] - p.off[T_G];
-  const size_t gid = (size_t)task_i * kEpiThreads + e.tid, gstride = (size_t)nG * kEpiThreads;
-  // the four weight gradients as one list of float4 items; a thread keeps two items and, per item, four chunk loads
-  // in flight (the additions keep chunk order)
-  const size_t n2 = (size_t)p.P * p.P / 4, n1 = (size_t)p.P * p.H / 4, ntot = 2 * (n2 + n1);
-  auto locate = [&](size_t item, const float4*& src, float4*& dst, size_t& n4, int& nch) {
-    const int t = item >= n2 + n1;
-    size_t i = item - (t ? n2 + n1 : 0);
-    const int c0 = t ? p.nch[0] : 0;
-    nch = p.nch[t];
-    if (i < n2) {
-      n4 = n2;
-      src = reinterpret_cast<const float4*>(p.part2) + (size_t)c0 * n2 + i;
-      dst = reinterpret_cast<float4*>(p.dW2[t]) + i;
-    } else {
-      i -= n2;
-      n4 = n1;
-      src = reinterpret_cast<const float4*>(p.part1) + (size_t)c0 * n1 + i;
-      dst = reinterpret_cast<float4*>(p.dW1[t]) + i;
+  // A weight gradient pair (both towers) is a list of float4 items cut into chunks of 512 that the CTAs CLAIM (one
+  // atomic per chunk): a CTA that arrives early takes more of them, the CTA that finishes the last contraction task
+  // finds little left.  A thread keeps two items and, per item, four chunk loads in flight; the additions keep the
+  // order of the batch-row chunks, so the sums do not depend on who computes them.
+  volatile int* claim_s = reinterpret_cast<volatile int*>(e.cs_s);  // (the column-sum staging is idle in this phase)
+  int round = 0;
+  auto sum_pairs = [&](unsigned* claim, const float* part, float* const (&dW)[2], size_t n4) {
+    auto locate = [&](size_t item, const float4*& src, float4*& dst, int& nch) {
+      const int t = item >= n4;
+      const size_t i = item - (t ? n4 : 0);
+      nch = p.nch[t];
+      src = reinterpret_cast<const float4*>(part) + (size_t)(t ? p.nch[0] : 0) * n4 + i;
+      dst = reinterpret_cast<float4*>(dW[t]) + i;
+    };
+    const size_t ntot = 2 * n4;
+    const int nchunks = (int)((ntot + 2 * kEpiThreads - 1) / (2 * kEpiThreads));
+    for (;;) {
+      if (e.tid == 0) claim_s[round & 1] = (int)atomicAdd(claim, 1u);
+      epi_bar();
+      const int c = claim_s[round & 1];
+      ++round;
+      if (c >= nchunks) break;
+      const size_t it = (size_t)c * 2 * kEpiThreads + e.tid;
+      if (it >= ntot) continue;
+      const float4* src[2];
+      float4* dst[2];
+      int nch[2];
+      const bool two = it + kEpiThreads < ntot;
+      locate(it, src[0], dst[0], nch[0]);
+      locate(two ? it + kEpiThreads : it, src[1], dst[1], nch[1]);
+      float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      const int nmax = max(nch[0], nch[1]);
+      for (int j = 0; j < nmax; j += 4) {
+        float4 t[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            t[u][c4] = (j + c4 < nch[u]) ? __ldcg(src[u] + (size_t)(j + c4) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            if (j + c4 < nch[u]) acc[u] = add4(acc[u], t[u][c4]);
+      }
+      emit4(p, k, dst[0], acc[0]);
+      if (two) emit4(p, k, dst[1], acc[1]);
     }
   };
-  for (size_t it = gid; it < ntot; it += 2 * gstride) {
-    const float4* src[2];
-    float4* dst[2];
-    size_t n4[2];
-    int nch[2];
-    const bool two = it + gstride < ntot;
-    locate(it, src[0], dst[0], n4[0], nch[0]);
-    locate(two ? it + gstride : it, src[1], dst[1], n4[1], nch[1]);
-    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-    const int nmax = max(nch[0], nch[1]);
-    for (int j = 0; j < nmax; j += 4) {
-      float4 t[2][4];
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          t[u][k] = (j + k < nch[u]) ? __ldcg(src[u] + (size_t)(j + k) * n4[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (j + k < nch[u]) acc[u] = add4(acc[u], t[u][k]);
-    }
-    emit4(p, k, dst[0], acc[0]);
-    if (two) emit4(p, k, dst[1], acc[1]);
-  }
+  sum_pairs(p.ctr + 6, p.part2, p.dW2, (size_t)p.P * p.P / 4);
+  // phase B: everything else has signalled
+  if (e.tid == 0) wait_counter(p.ctr + 1, p.total_signals);
+  epi_bar();
+  sum_pairs(p.ctr + 7, p.part1, p.dW1, (size_t)p.P * p.H / 4);
   // bias gradients: one output per warp at a time, the lanes take the row-tile partials (lane-strided, then a fixed
   // xor tree), so every CTA shares this tail instead of the first few
   {
@@ -1157,6 +1170,7 @@ int chain_sm100(const StepSm100& s, bool after_gather, cudaStream_t st) {
   p.off[0] = 0;
   for (int k = 0; k < T_COUNT; ++k) p.off[k + 1] = p.off[k] + count[k];
   p.total_signals = (unsigned)(count[T_F2L] + count[T_DZ] + count[T_DW2] + count[T_DW1]);
+  p.dw2_signals = (unsigned)count[T_DW2];
   p.stages = chain_stages();
   // weights of both towers -> bf16 terms (+ transposes for the backward contractions); the first-layer weights come
   // first in the flat pass: layer 1 starts as soon as THEY are split (counter 0), the rest signals counter 2
