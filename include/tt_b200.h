@@ -346,6 +346,10 @@ int tt_split_bf16_terms(const float* x, int rows, int cols, void* hi, void* lo, 
 int tt_debug_step_buffer(void* ws, int B, int Lq, int Ld, int H, int P, int vocab, int precision, int train_table,
                          const char* name, void** ptr);
 int tt_ubench_l2_read(const void* buf, size_t bytes, int iters, int ctas_per_sm, void* sink, tt_stream_t stream);
+/* Self-test of the MN-major tcgen05 operand path (the persistent chain kernel's weight gradients contract over the
+ * batch rows of row-major activations without transposed copies): D[128,128] fp32 = sum_k A[k][m] * B[k][n] for
+ * A, B [K,128] bf16 row-major on the device, K a multiple of 64.  One CTA; for tests.                           */
+int tt_selftest_mn_major(const void* A, const void* B, int K, float* D, tt_stream_t stream);
 
 #ifdef __cplusplus
 }

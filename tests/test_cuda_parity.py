@@ -930,3 +930,20 @@ def test_scan_streaming_regime_is_repeatable_under_stress(tt):
     for q, r in zip(*np.nonzero(got_i != i32[:, :10])):
         gaps = [abs(s32[q, r] - s32[q, r + 1])] + ([abs(s32[q, r] - s32[q, r - 1])] if r else [])
         assert min(gaps) <= 1e-5, (q, r, gaps)
+
+
+@pytest.mark.parametrize("K", [64, 320])
+def test_mn_major_tcgen05_operands_are_exact(tt, K):
+    """The persistent chain kernel reads row-major activations as MN-major tcgen05 operands (no transposed copies).
+    D = A^T B over small integers is exact in bf16 x bf16 -> fp32, so the device product must equal the host's bit for
+    bit; a wrong leading / stride offset or K step in the shared-memory descriptor scrambles it."""
+    from two_towers_overlords_b200 import _native as N
+
+    g = torch.Generator().manual_seed(K)
+    A = (torch.randint(-8, 9, (K, 128), generator=g).float() / 8).to(torch.bfloat16)
+    B = (torch.randint(-6, 7, (K, 128), generator=g).float() / 4).to(torch.bfloat16)
+    want = A.float().t() @ B.float()
+    Ad, Bd = A.to(DEV), B.to(DEV)
+    D = torch.empty(128, 128, dtype=torch.float32, device=DEV)
+    N.check(N.load().tt_selftest_mn_major(N.ptr(Ad), N.ptr(Bd), K, N.ptr(D), N.stream()), "tt_selftest_mn_major")
+    assert torch.equal(D.cpu(), want)

@@ -132,6 +132,7 @@ _SIGNATURES = {
     "tt_debug_step_buffer": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_char_p,
                                      POINTER(c_void_p)]),
     "tt_ubench_l2_read": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
+    "tt_selftest_mn_major": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "tt_peer_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
     "tt_peer_topk_merge": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),

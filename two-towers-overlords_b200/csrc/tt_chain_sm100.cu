@@ -22,7 +22,7 @@
 // over the weights' rows) read that operand as it lies in memory — TMA boxes of 64 k-rows x 64 elements, 128-byte
 // swizzle — and describe it to tcgen05.mma as MN-MAJOR (instruction-descriptor bits 15 / 16; shared-memory descriptor:
 // leading offset 8192 B between the two 64-element boxes of a 128-wide tile, stride offset 1024 B between groups of 8
-// k-rows, 2048 B per K = 16 step; checked bit-exact against the host by scripts/ubench/mn_major_test.cu).
+// k-rows, 2048 B per K = 16 step; checked bit-exact against the host by tt_selftest_mn_major / tests/test_cuda_parity.py).
 //
 // Warp roles per CTA: warp 0 = TMA producer (also waits for a task's dependencies), warp 1 = TMEM owner + single-thread
 // tcgen05.mma issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, 64 columns each).  The accumulators form
