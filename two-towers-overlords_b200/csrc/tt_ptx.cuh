@@ -247,7 +247,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 }
 // MN-major operand, 128-byte swizzle: the tile is a row of [64 k-rows x 64 elements] boxes (one per 64 elements of the
 // M / N extent, `box_bytes` apart = leading offset); inside a box, groups of 8 k-rows are 1024 B apart (stride offset).
-// A K = 16 step advances the start address by two such groups (2048 B).  Verified by scripts/ubench/mn_major_test.cu.
+// A K = 16 step advances the start address by two such groups (2048 B).  Verified by tt_selftest_mn_major (tt_ubench.cu).
 __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t box_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
