@@ -571,10 +571,17 @@ __device__ void epi_f2l(const ChainParams& p, EpiCtx& e, int task_i) {
     qp = fmaf(a, b, qp);
     qn = fmaf(a, d, qn);
   }
-  const int nslots = 2 * p.NCF;
-  if (seg == 0) {
-    float* sp = p.stat_part + ((size_t)(r * nslots + c * 2 + e.hf) * 5) * 128 + row;
-    sp[0] = qq; sp[128] = pp; sp[256] = nn; sp[384] = qp; sp[512] = qn;
+  // one slot of partial sums per column tile: the two column halves of the tile meet in shared memory first
+  const int nslots = p.NCF;
+  float* xs = e.cs_s;  // [5][128] (the column-sum staging is idle until the stores below)
+  if (seg == 0 && e.hf == 1) {
+    xs[row] = qq; xs[128 + row] = pp; xs[256 + row] = nn; xs[384 + row] = qp; xs[512 + row] = qn;
+  }
+  epi_bar();
+  if (seg == 0 && e.hf == 0) {
+    float* sp = p.stat_part + ((size_t)(r * nslots + c) * 5) * 128 + row;
+    sp[0] = qq + xs[row]; sp[128] = pp + xs[128 + row]; sp[256] = nn + xs[256 + row]; sp[384] = qp + xs[384 + row];
+    sp[512] = qn + xs[512 + row];
     __threadfence();
   }
   epi_bar();
@@ -586,9 +593,19 @@ __device__ void epi_f2l(const ChainParams& p, EpiCtx& e, int task_i) {
   trace_ev(e, 3);
   // ---- the whole row's sums, slot order fixed (identical in every task of this row tile) ------------------------
   qq = pp = nn = qp = qn = 0.f;
-  for (int s = 0; s < nslots; ++s) {
-    const float* sp = p.stat_part + ((size_t)(r * nslots + s) * 5) * 128 + row;
-    qq += __ldcg(sp); pp += __ldcg(sp + 128); nn += __ldcg(sp + 256); qp += __ldcg(sp + 384); qn += __ldcg(sp + 512);
+  for (int s0 = 0; s0 < nslots; s0 += 4) {  // four slots (20 loads) in flight; the additions keep slot order
+    float v[4][5];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* sp = p.stat_part + ((size_t)(r * nslots + min(s0 + u, nslots - 1)) * 5) * 128 + row;
+#pragma unroll
+      for (int w = 0; w < 5; ++w) v[u][w] = __ldcg(sp + 128 * w);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (s0 + u < nslots) {
+        qq += v[u][0]; pp += v[u][1]; nn += v[u][2]; qp += v[u][3]; qn += v[u][4];
+      }
   }
   const float nq = sqrtf(qq), np_ = sqrtf(pp), nn_ = sqrtf(nn);
   const float cq = fmaxf(nq, kCosEps), cp = fmaxf(np_, kCosEps), cn = fmaxf(nn_, kCosEps);
