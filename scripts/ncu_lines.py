@@ -22,7 +22,7 @@ kernel = rows[0][1]
 hdr = rows[1]
 iA, iS = hdr.index("Address"), hdr.index("# Samples")
 # the function's section in the disassembly
-fn = re.search(r"(\w+)\(", kernel).group(1)
+fn = re.search(r"::(\w+)(?:<.*>)?\(", kernel).group(1)
 cur, off2line, active = None, {}, False
 for ln in sass.split("\n"):
     if ln.startswith("//---") and ".text." in ln:
