@@ -61,8 +61,9 @@ def peaks():
 # --------------------------------------------------------------------------------------------------
 # synthetic inputs (same generator for both arms)
 # --------------------------------------------------------------------------------------------------
-def token_sets(n_sets: int, B: int, seed: int, ids_dtype, mask_dtype, pin: bool):
-    """n_sets x (q_ids,q_mask,p_ids,p_mask,n_ids,n_mask): shape U, negatives = in-batch derangement of the positives."""
+def token_sets(n_sets: int, B: int, seed: int, ids_dtype, mask_dtype, pin: bool, neg_index: list = None):
+    """n_sets x (q_ids,q_mask,p_ids,p_mask,n_ids,n_mask): shape U, negatives = in-batch derangement of the positives
+    (neg_index, when given, receives one int32 [B] tensor per set: negative i is positive neg_index[i])."""
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n_sets):
@@ -70,6 +71,8 @@ def token_sets(n_sets: int, B: int, seed: int, ids_dtype, mask_dtype, pin: bool)
         p = torch.randint(999, VOCAB, (B, LD), generator=g, dtype=torch.int64)
         shift = int(torch.randint(1, B, (1,), generator=g)) if B > 1 else 0
         n = torch.roll(p, shift, 0)  # negative_i = positive_{i-shift}: no fixed point
+        if neg_index is not None:
+            neg_index.append(torch.roll(torch.arange(B, dtype=torch.int32), shift, 0))
         ts = []
         for ids in (q, p, n):
             ts += [ids.to(ids_dtype), torch.ones(ids.shape, dtype=mask_dtype)]
@@ -457,6 +460,7 @@ def run_b200(args):
     torch.cuda.empty_cache()
     chain_variant = run_chain_variant(dev, args, ids_dtype, mask_dtype, host_packed) if (world == 1 and not args.no_chain_variant) else None
     backbone_leg = run_backbone_leg(dev, args) if (world == 1 and not args.no_backbone) else None
+    reuse_leg = run_negative_reuse_leg(dev, args, ids_dtype, mask_dtype) if (world == 1 and not args.no_chain_variant) else None
     config2 = run_config2(dev, world, rank, args, l2_peak=l2_peak) if not args.no_config2 else None
     epoch_leg = run_epoch_leg(dev, world, rank, args) if not args.no_epoch else None
     torch.cuda.empty_cache()
@@ -476,6 +480,7 @@ def run_b200(args):
                         "dp_exchange": exchange_kind, "token_dtypes": f"ids {args.ids_dtype}, mask u8"},
             "graph_captures_in_timed_region": captures_in_timed, "dp_check": dp_check, "config2": config2,
             "epoch_leg": epoch_leg, "projection_chain": chain_variant, "full_backbone": backbone_leg,
+            "in_batch_negative_reuse": reuse_leg,
             "dp_exchange_us": exchange_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
@@ -554,6 +559,62 @@ def run_backbone_leg(dev, args, B=256, steps=6):
         except Exception as ex:  # the leg is informative: a missing transformers install must not fail the bench
             out["cpu_baseline"] = {"unavailable": repr(ex)}
     del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# in-batch negatives named by index: every positive document is pooled once
+# --------------------------------------------------------------------------------------------------
+def run_negative_reuse_leg(dev, args, ids_dtype, mask_dtype, steps=40, n_sets=16):
+    """configs[1] again, the SAME batches as the headline leg's generator makes (negative i = positive neg_index[i], as
+    the reference's batcher draws them, backend/data.py:113-137), but the trainer is told the indices
+    (tt_step_args.neg_index): the pooled gather then visits each positive once and copies its row to the negatives
+    that name it.  Bit-identical results (tests/test_cuda_parity.py::test_in_batch_negative_reuse_gives_the_same_bits);
+    a third of the table rows are not read a second time.  NOT the headline: that leg gathers all three token
+    tensors like the reference's three tower calls."""
+    from two_towers_overlords_b200 import TwoTowersModel
+    from two_towers_overlords_b200.training import FusedTrainer
+
+    torch.manual_seed(0)
+    model = TwoTowersModel(projection_dim=P_DIM, precision=args.precision).to(dev)
+    tr = FusedTrainer(model, MARGIN, LR, B_PER_GPU, LQ, LD, precision=args.precision, ids_dtype=ids_dtype,
+                      mask_dtype=mask_dtype, token_slots=n_sets, in_batch_negatives=True)
+    negs = []
+    sets = token_sets(n_sets, B_PER_GPU, 777, ids_dtype, mask_dtype, pin=False, neg_index=negs)
+    for slot, (ts, ng) in enumerate(zip(sets, negs)):
+        tr.load_packed(tr.pack_host_tokens(ts, pin=False), slot)
+        tr.load_neg_index(ng, slot)
+    tr.prepare()
+    for i in range(n_sets):
+        tr.step(i % n_sets, (i + 1) % n_sets)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        tr.step(i % n_sets, (i + 1) % n_sets)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    for _ in range(3):
+        tr._fwd_bwd(0, 1, 0)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(steps):
+        tr._fwd_bwd(i % n_sets, 1, 0)
+    ev1.record()
+    torch.cuda.synchronize()
+    pool_us = ev0.elapsed_time(ev1) / steps * 1e3
+    err = int(tr.step_obj.err.item())
+    out = {"workload": "configs[1] with the in-batch negatives named by index (tt_step_args.neg_index): every positive "
+                       "document is pooled once, its row copied to the negatives that name it",
+           "ms_per_step": ms, "triplets_per_s": B_PER_GPU / (ms * 1e-3), "gather_us": pool_us,
+           "launches_per_step": int(tr.kernel_launches_per_step or 0), "err_flag": err,
+           "loss": float(tr.loss_view[0].item()),
+           "note": f"{n_sets} rotating token batches ({n_sets * 3.34:.0f} MB); results bit-identical to gathering the negatives' "
+                   "tokens; run_training uses this with the device feeder on one GPU (TT_NEG_REUSE=0 turns it off)"}
+    tr.close()
+    del tr, model
     torch.cuda.empty_cache()
     return out
 
@@ -816,8 +877,9 @@ def run_epoch_leg(dev, world, rank, args):
     tok = train_ds.tokenizer()
     tok.add(val_ds.tokenizer())
     m.query_tower.tokenizer = m.document_tower.tokenizer = tok
+    reuse = world == 1 and os.environ.get("TT_NEG_REUSE", "1") != "0"  # as run_training wires it (one GPU, device feeder)
     tr = FusedTrainer(m, MARGIN, LR, B_PER_GPU, LQ, LD, precision=args.precision, world_size=world, rank=rank,
-                      token_slots=2)
+                      token_slots=2, in_batch_negatives=reuse)
     feeder = DeviceTripletFeeder(train_ds, gb, LQ, LD, dev, rank=rank, world_size=world, seed=17)
     tr.prepare(2)
     steps = len(feeder)
@@ -844,6 +906,7 @@ def run_epoch_leg(dev, world, rank, args):
                        "device-assembled batches, NDCG@10 evaluation at the end of the epoch",
            "triplets": steps * gb, "global_batch": gb, "steps": steps, "epoch_ms": train_ms,
            "triplets_per_s": steps * gb / (train_ms * 1e-3), "avg_loss": avg, "eval_ms": eval_ms, "val_ndcg_10": ndcg,
+           "in_batch_negative_reuse": bool(reuse),
            "note": "includes per-step batch assembly on the device and the host-side launch loop; evaluate_model = "
                    "sampling + sharded document encode + candidate scoring + NDCG@10 (20 queries, reference defaults)"}
     del tr, m, feeder

@@ -176,6 +176,14 @@ typedef struct tt_step_args {
                         gradient reduction, optimiser); 2 = one kernel per contraction (small kernels a concurrent
                         look-ahead gather can slip between); 0 = library default: TT_CHAIN env (1 / 0 = per-kernel),
                         else 1.  Keep the same choice for the TT_STEP_FRONT and TT_STEP_BACK calls of one step.   */
+  /* optional in-batch negatives (NULL = the negatives are gathered from n_ids / n_mask like any document).
+   * The reference's batcher draws every negative among the OTHER items' positive documents of the same batch
+   * (backend/data.py:113-137), so negative row i is the same token sequence as positive row neg_index[i]
+   * (0 <= neg_index[i] < B, int32 on the device).  Given the indices, the pooled gather visits every positive
+   * once and writes its pooled row to the negative rows that name it — the same bits as gathering the same tokens
+   * again, for half the document rows read; n_ids / n_mask are not read then.  Frozen tables only.  An index out
+   * of range raises err_flag.                                                                                  */
+  const int32_t* neg_index;
 } tt_step_args;
 #define TT_STEP_FRONT 1
 #define TT_STEP_BACK 2

@@ -947,3 +947,73 @@ def test_mn_major_tcgen05_operands_are_exact(tt, K):
     D = torch.empty(128, 128, dtype=torch.float32, device=DEV)
     N.check(N.load().tt_selftest_mn_major(N.ptr(Ad), N.ptr(Bd), K, N.ptr(D), N.stream()), "tt_selftest_mn_major")
     assert torch.equal(D.cpu(), want)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("chain", ["1", "0"])
+def test_in_batch_negative_reuse_gives_the_same_bits(tt, monkeypatch, precision, chain):
+    """The reference's batcher draws every negative among the other items' positives (backend/data.py:113-137).  Given
+    their indices (tt_step_args.neg_index) the pooled gather visits each positive once and copies its row to the
+    negatives that name it: pooled rows, loss, every gradient and the weights after three Adam steps must be bit-identical
+    to gathering the negatives' own tokens.  One positive is named by three negatives, one by none; ragged masks."""
+    monkeypatch.setenv("TT_CHAIN", chain)
+    B, Lq, Ld, P, V = 300, 16, 48, 64, 2048
+    g = torch.Generator().manual_seed(5)
+
+    def batch(seed):
+        b = O.synth_triplet_batch(B, Lq, Ld, "Z", seed=seed, vocab=V)
+        q_ids, q_mask, p_ids, p_mask, _, _ = b.astuple()
+        Ld_ = p_ids.shape[1]
+        neg = torch.roll(torch.arange(B), 7)
+        neg[:3] = 11  # positive 11 is the negative of three items (and of a fourth through the roll)
+        return (q_ids, q_mask, p_ids, p_mask, p_ids[neg].clone(), p_mask[neg].clone()), neg.to(torch.int32), q_ids.shape[1], Ld_
+
+    batches = [batch(70 + i) for i in range(3)]
+    Lq_, Ld_ = max(b[2] for b in batches), max(b[3] for b in batches)
+
+    def pad(t, L):
+        return torch.nn.functional.pad(t, (0, L - t.shape[1]))
+
+    def run(reuse):
+        torch.manual_seed(3)
+        m = tt.TwoTowersModel(projection_dim=P, vocab_size=V, precision=precision).to(DEV)
+        tr = tt.training.FusedTrainer(m, 0.3, 1e-3, B, Lq_, Ld_, precision=precision, ids_dtype=torch.int64,
+                                      mask_dtype=torch.int64, in_batch_negatives=reuse)
+        outs = []
+        for toks, neg, _, _ in batches:
+            toks = tuple(pad(t, Lq_ if i < 2 else Ld_) for i, t in enumerate(toks))
+            if reuse:  # the negatives' own token tensors are never read: poison them
+                toks = toks[:4] + (torch.full_like(toks[4], V - 1), torch.ones_like(toks[5]))
+                tr.load_neg_index(neg)
+            tr.load_packed(tr.pack_host_tokens(toks, pin=False))
+            loss = tr.step()
+            outs.append((float(loss.item()), tr.step_obj.pooled_rows().clone(), [g_.clone() for g_ in tr.g_views]))
+        torch.cuda.synchronize()
+        assert int(tr.step_obj.err.item()) == 0
+        w = tr.flat_p.clone()
+        tr.close()
+        return outs, w
+
+    a, wa = run(False)
+    b, wb = run(True)
+    for (la, xa, ga), (lb, xb, gb) in zip(a, b):
+        assert la == lb
+        assert torch.equal(xa, xb)
+        assert all(torch.equal(u, v) for u, v in zip(ga, gb))
+    assert torch.equal(wa, wb)
+
+
+def test_in_batch_negative_index_out_of_range_raises_the_error_flag(tt):
+    B, Lq, Ld, P, V = 64, 8, 16, 64, 512
+    torch.manual_seed(0)
+    m = tt.TwoTowersModel(projection_dim=P, vocab_size=V, precision="bf16x3").to(DEV)
+    tr = tt.training.FusedTrainer(m, 0.3, 1e-3, B, Lq, Ld, precision="bf16x3", ids_dtype=torch.int64,
+                                  mask_dtype=torch.int64, in_batch_negatives=True)
+    tr.load_packed(tr.pack_host_tokens(O.synth_triplet_batch(B, Lq, Ld, "U", seed=1, vocab=V).astuple(), pin=False))
+    neg = torch.roll(torch.arange(B), 1)
+    neg[5] = B  # not a row of this batch
+    tr.load_neg_index(neg)
+    tr.step()
+    torch.cuda.synchronize()
+    assert int(tr.step_obj.err.item()) != 0
+    tr.close()

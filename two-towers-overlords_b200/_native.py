@@ -65,6 +65,7 @@ class StepArgs(ctypes.Structure):
         ("adam_n", c_size_t),
         ("adam_lr", c_float), ("adam_beta1", c_float), ("adam_beta2", c_float), ("adam_eps", c_float),
         ("chain", c_int),
+        ("neg_index", c_void_p),
     ]
 
 

@@ -260,6 +260,14 @@ extern "C" int tt_triplet_step(const tt_step_args* a, tt_stream_t stream) {
   pp.cnt = w.cnt;
   pp.nrm = w.nrm;
   pp.err = a->err_flag;
+  if (a->neg_index) {  // in-batch negatives: the n rows are copies of the p rows they name
+    TT_REQUIRE(!train_table, "tt_triplet_step: neg_index needs frozen tables (the table gradient walks the negatives' tokens)");
+    pp.nseg = 2;
+    pp.alias = a->neg_index;
+    pp.alias_n = B;
+    pp.alias_src_row0 = B;
+    pp.alias_dst_row0 = 2 * B;
+  }
 
   float* dxhat = train_table ? w.dxhat : nullptr;
   bool adam_done = false;

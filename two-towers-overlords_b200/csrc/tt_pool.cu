@@ -207,36 +207,68 @@ __global__ void __launch_bounds__(kPoolThreads) pool_fwd_kernel(const PoolParams
   const float dn = fmaxf(nrm, 1e-12f);  // F.normalize eps, model.py:56
 
   const int row_out = sg.row0 + b;
-  if (owner) {
-    const float4 x = make_float4(m.x / dn, m.y / dn, m.z / dn, m.w / dn);
-    *reinterpret_cast<float4*>(p.xhat + (size_t)row_out * H + tid * 4) = x;
-    if (p.x_hi) {  // operands of the tensor-core projection: bf16 hi/lo split, row-major + transposed
-      const float xv[4] = {x.x, x.y, x.z, x.w};
-      __nv_bfloat16 hi[4], lo[4];
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (owner) x = make_float4(m.x / dn, m.y / dn, m.z / dn, m.w / dn);
+  // every output of one pooled row (owner threads: 4 columns each; thread 0: the count and the norm)
+  auto emit_row = [&](int row) {
+    if (owner) {
+      *reinterpret_cast<float4*>(p.xhat + (size_t)row * H + tid * 4) = x;
+      if (p.x_hi) {  // operands of the tensor-core projection: bf16 hi/lo split, row-major + transposed
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+        __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) split_bf16(xv[c], hi[c], lo[c]);
-      *reinterpret_cast<uint2*>(p.x_hi + (size_t)row_out * H + tid * 4) = *reinterpret_cast<uint2*>(hi);
-      *reinterpret_cast<uint2*>(p.x_lo + (size_t)row_out * H + tid * 4) = *reinterpret_cast<uint2*>(lo);
-      if (p.x_lo2) {
-        __nv_bfloat16 l2[4];
+        for (int c = 0; c < 4; ++c) split_bf16(xv[c], hi[c], lo[c]);
+        *reinterpret_cast<uint2*>(p.x_hi + (size_t)row * H + tid * 4) = *reinterpret_cast<uint2*>(hi);
+        *reinterpret_cast<uint2*>(p.x_lo + (size_t)row * H + tid * 4) = *reinterpret_cast<uint2*>(lo);
+        if (p.x_lo2) {
+          __nv_bfloat16 l2[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          l2[c] = __float2bfloat16_rn((xv[c] - __bfloat162float(hi[c])) - __bfloat162float(lo[c]));
-        *reinterpret_cast<uint2*>(p.x_lo2 + (size_t)row_out * H + tid * 4) = *reinterpret_cast<uint2*>(l2);
-      }
-      if (p.xt_hi) {
-        const int tcol = row_out + (row_out >= p.t_split_row ? p.t_shift : 0);
+          for (int c = 0; c < 4; ++c)
+            l2[c] = __float2bfloat16_rn((xv[c] - __bfloat162float(hi[c])) - __bfloat162float(lo[c]));
+          *reinterpret_cast<uint2*>(p.x_lo2 + (size_t)row * H + tid * 4) = *reinterpret_cast<uint2*>(l2);
+        }
+        if (p.xt_hi) {
+          const int tcol = row + (row >= p.t_split_row ? p.t_shift : 0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          p.xt_hi[(size_t)(tid * 4 + c) * p.ldt + tcol] = hi[c];
-          p.xt_lo[(size_t)(tid * 4 + c) * p.ldt + tcol] = lo[c];
+          for (int c = 0; c < 4; ++c) {
+            p.xt_hi[(size_t)(tid * 4 + c) * p.ldt + tcol] = hi[c];
+            p.xt_lo[(size_t)(tid * 4 + c) * p.ldt + tcol] = lo[c];
+          }
         }
       }
     }
+    if (tid == 0) {
+      if (p.cnt) p.cnt[row] = cnt;
+      if (p.nrm) p.nrm[row] = nrm;
+    }
+  };
+  emit_row(row_out);
+  if (p.alias && (int)blockIdx.x < p.alias_n && tid == 0) {  // every alias index is range-checked by some CTA
+    const int a = __ldg(p.alias + blockIdx.x);
+    if ((a < 0 || a >= p.alias_n) && p.err) atomicExch(p.err, 1);
   }
-  if (tid == 0) {
-    if (p.cnt) p.cnt[row_out] = cnt;
-    if (p.nrm) p.nrm[row_out] = nrm;
+  // In-batch negatives (backend/data.py:113-137: a negative IS another item's positive document): rows that alias
+  // this one get the same bits instead of a second gather of the same tokens.
+  if (p.alias && row_out >= p.alias_src_row0 && row_out < p.alias_src_row0 + p.alias_n) {
+    constexpr int kMatchCap = 32;
+    __shared__ int s_match[kMatchCap];
+    __shared__ int s_nmatch;
+    const int j = row_out - p.alias_src_row0;
+    if (tid == 0) s_nmatch = 0;
+    __syncthreads();
+    for (int i = tid; i < p.alias_n; i += kPoolThreads)
+      if (__ldg(p.alias + i) == j) {
+        const int k = atomicAdd(&s_nmatch, 1);
+        if (k < kMatchCap) s_match[k] = i;
+      }
+    __syncthreads();
+    const int nm = s_nmatch;
+    if (nm <= kMatchCap) {
+      for (int k = 0; k < nm; ++k) emit_row(p.alias_dst_row0 + s_match[k]);
+    } else {  // (a document drawn as the negative of more than 32 items of one batch: plain rescan, CTA-uniform)
+      for (int i = 0; i < p.alias_n; ++i)
+        if (__ldg(p.alias + i) == j) emit_row(p.alias_dst_row0 + i);
+    }
   }
 }
 

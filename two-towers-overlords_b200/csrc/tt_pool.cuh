@@ -30,6 +30,10 @@ struct PoolParams {
   // start at a 64-aligned column so each tower's K range is its own TMA tensor
   int t_split_row, t_shift;
   int share_sm;  // 1: this launch runs beside other kernels (pipelined step): cap the resident CTAs per SM
+  // optional row aliases: output row alias_dst_row0 + i is a copy of output row alias_src_row0 + alias[i], i < alias_n
+  // (in-batch negatives: negative i is the positive document of item alias[i]); nullptr = none
+  const int* alias;
+  int alias_n, alias_src_row0, alias_dst_row0;
 };
 
 constexpr int kPoolSharePadBytes = 0;  // default cap (bytes of unused dynamic smem per CTA); tuned on B200, see tt_pool.cu

@@ -360,12 +360,15 @@ class DeviceTripletFeeder:
         q_ids, q_mask, p_ids, p_mask, n_ids, n_mask = trainer.tok_slots[slot]
         assert tuple(q_ids.shape) == (self.per, self.Lq) and tuple(p_ids.shape) == (self.per, self.Ld)
         order = self.order[step * self.gb: (step + 1) * self.gb]
+        # a trainer that reuses the positives' pooled rows for the in-batch negatives wants their indices in its slot
+        neg_bufs = getattr(trainer, "neg_bufs", None)
+        neg_ptr = N.ptr(neg_bufs[slot]) if neg_bufs is not None else (N.ptr(self.neg) if want_neg else None)
         step_seed = (self.seed * 0x9E3779B1 + self.epoch * 0x85EBCA77 + step) & 0xFFFFFFFFFFFFFFFF
         N.check(N.load().tt_assemble_triplets(
             ctypes.byref(self.q_desc), ctypes.byref(self.d_desc), N.ptr(self.pair_q), N.ptr(self.pair_d),
             N.ptr(self.pair_qid), order.data_ptr(), self.gb, self.rank * self.per, self.per, step_seed, self.Lq, self.Ld,
             N.ptr(q_ids), N.ptr(q_mask), N.ptr(p_ids), N.ptr(p_mask), N.ptr(n_ids), N.ptr(n_mask), N.dtype_code(q_ids),
-            N.dtype_code(q_mask), N.ptr(self.neg) if want_neg else None, N.ptr(self.err), N.stream()),
+            N.dtype_code(q_mask), neg_ptr, N.ptr(self.err), N.stream()),
             "tt_assemble_triplets")
 
     def check(self):

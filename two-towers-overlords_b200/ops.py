@@ -292,6 +292,19 @@ class TripletStep:
         nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
         return self.ws[off: off + nbytes].view(dtype).view(rows, cols)
 
+    def set_neg_index(self, slot: int, neg_index: Optional[torch.Tensor]):
+        """In-batch negatives for `slot` (tt_step_args.neg_index): int32 [B] on the device, negative row i is the same
+        document as positive row neg_index[i]; its pooled row is then a copy instead of a second gather.  None: the
+        negatives are gathered from their own token tensors."""
+        a = self.slots[slot]
+        if neg_index is None:
+            a.neg_index = None
+            return
+        assert not self.train_table, "neg_index needs frozen tables"
+        assert neg_index.dtype == torch.int32 and neg_index.is_cuda and tuple(neg_index.shape) == (self.shape[0],)
+        a.neg_index = N.ptr(neg_index)
+        self._keep.append(neg_index)
+
     def set_chain(self, mode: int):
         """tt_step_args.chain: 0 = library default (TT_CHAIN env, else the persistent kernel), 1 = persistent chain
         kernel, 2 = one kernel per contraction."""

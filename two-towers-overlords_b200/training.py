@@ -131,7 +131,7 @@ class FusedTrainer:
                  precision: Optional[str] = None, world_size: int = 1, rank: int = 0, use_graph: bool = True,
                  betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, ids_dtype=torch.int32,
                  mask_dtype=torch.uint8, token_slots: int = 1, exchange: Optional[str] = None,
-                 exchange_ctas: int = 0):
+                 exchange_ctas: int = 0, in_batch_negatives: bool = False):
         qt, dt = model.query_tower, model.document_tower
         self.model = model
         self.device = qt.pretrained_model.device
@@ -242,6 +242,20 @@ class FusedTrainer:
                              self.betas, self.eps)
             self.step_objs.append(so)
         self.step_obj = self.step_objs[0]
+        # In-batch negatives (the reference's batcher, backend/data.py:113-137): negative i IS positive neg_index[i], so
+        # its pooled row is copied instead of gathered a second time (tt_step_args.neg_index).  One int32 [B] buffer per
+        # token slot (static addresses: the step graphs read them); fill them with load_neg_index() / the device feeder.
+        self.in_batch_negatives = bool(in_batch_negatives)
+        self.neg_bufs = None
+        if self.in_batch_negatives:
+            if self.train_table:
+                raise ValueError("in_batch_negatives needs frozen tables")
+            if world_size > 1:
+                raise ValueError("in_batch_negatives: the negatives of a data-parallel slice name documents of other ranks")
+            self.neg_bufs = [torch.zeros(batch_size, dtype=torch.int32, device=dev) for _ in self.tok_slots]
+            for so in self.step_objs:
+                for slot, buf in enumerate(self.neg_bufs):
+                    so.set_neg_index(slot, buf)
         self.use_graph = use_graph
         self.graphs = {}       # (slot, next_slot, parity) -> CUDAGraph
         self.graph_opt = None  # NCCL mode: Adam after the all-reduce
@@ -301,6 +315,10 @@ class FusedTrainer:
         for dst, src in zip(self.tok_slots[slot], (q.input_ids, q.attention_mask, p.input_ids, p.attention_mask,
                                                    n.input_ids, n.attention_mask)):
             dst.copy_(src, non_blocking=True)
+
+    def load_neg_index(self, neg_index: torch.Tensor, slot: int = 0):
+        """Indices of the in-batch negatives of the batch in `slot` (int [B]; host or device), async on the current stream."""
+        self.neg_bufs[slot].copy_(neg_index.to(torch.int32), non_blocking=True)
 
     def _fwd_bwd(self, slot: int = 0, phases: int = 0, parity: int = 0, optimise: bool = False):
         self.step_objs[parity].run(slot, phases, optimise=optimise)
@@ -973,9 +991,14 @@ def run_training(
         seed_box = [random.randrange(2 ** 31)]
         if world > 1:  # the epoch permutation and the in-batch negatives are functions of this seed: share rank 0's
             dist.broadcast_object_list(seed_box, src=0)
+        host_feeder = os.environ.get("TT_HOST_FEEDER") == "1" or len(train_ds) < 2 * batch_size
+        # the device feeder draws the in-batch negatives itself and hands their indices to the trainer, which then pools
+        # every positive document once (TT_NEG_REUSE=0: gather the negatives' tokens like any document)
+        reuse = (not host_feeder and world == 1 and os.environ.get("TT_NEG_REUSE", "1") != "0"
+                 and not model.query_tower.pretrained_model.table.requires_grad)
         trainer = FusedTrainer(model, margin, learning_rate, batch_size // world, token_slots=2, world_size=world,
-                               rank=rank)
-        if os.environ.get("TT_HOST_FEEDER") == "1" or len(train_ds) < 2 * batch_size:
+                               rank=rank, in_batch_negatives=reuse)
+        if host_feeder:
             # host-assembled batches (negatives drawn over the global batch, this rank's slice)
             token_dl = TokenTripletLoader(train_ds, batch_size, trainer.Lq, trainer.Ld, rank=rank, world_size=world,
                                           seed=seed_box[0])
