@@ -1016,8 +1016,9 @@ def run_scan(dev, world, rank, n_docs, n_queries, P, passes, precision="bf16"):
                              "traffic": ncu_traffic("scan_candidates_kernel_batched_100kq_8.8M")
                              if (n_local == 8_800_000 and P == 384 and n_queries == 100_000) else None,
                              "note": "whole pass (normalise + scan + refine/re-score + merge + NDCG); 2*Q*N_local*P "
-                                     "flops; traffic is DRAM bytes of the scan kernel (the corpus is re-streamed once "
-                                     "per wave of query tiles, L2 absorbs 70 %)"},
+                                     "flops; traffic is DRAM bytes of the scan kernel (cta_group::2 tiles on a shard this "
+                                     "long: each document tile is loaded once per CTA pair and multicast; the one-CTA "
+                                     "kernel moved 1.31 TB per pass)"},
         "roofline_streaming": {"bound": "hbm", "queries": 128, "achieved": stream_bytes / (ms_small * 1e-3) / 1e9,
                                "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s",
                                "frac": stream_bytes / (ms_small * 1e-3) / 1e9 / hbm_peak, "ms_per_pass": ms_small,

@@ -513,10 +513,13 @@ def test_scan_topk_fp32_vs_oracle(tt, Q, N, P, k):
     assert np.array_equal(top_i.cpu().numpy()[:3, : min(k, N)], ids[:, :k])
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
 @pytest.mark.parametrize("Q,N,P,k", [(1, 1000, 64, 10), (70, 4097, 384, 10), (200, 9950, 128, 16), (5, 7, 64, 10),
                                      (64, 65, 512, 1), (300, 50_000, 384, 10), (129, 20_001, 72, 10)])
-def test_scan_topk_tensor_core_vs_oracle(tt, Q, N, P, k):
-    """tcgen05 scan: bf16 candidate generation + exact fp32 re-score must return the fp32 ranking."""
+def test_scan_topk_tensor_core_vs_oracle(tt, monkeypatch, Q, N, P, k, pair):
+    """tcgen05 scan: bf16 candidate generation + exact fp32 re-score must return the fp32 ranking.  pair = 1 forces the
+    cta_group::2 kernel (256 queries per CTA pair, document tiles multicast) that long shards select by themselves."""
+    monkeypatch.setenv("TT_SCAN_PAIR", pair)
     gen = torch.Generator().manual_seed(Q * N + 1)
     Qe, De = torch.randn(Q, P, generator=gen), torch.randn(N, P, generator=gen)
     Qn, Qb = tt.ops.l2_normalize_rows(Qe.to(DEV), want_bf16=True)
@@ -547,9 +550,11 @@ def test_scan_tensor_core_exact_rescan_of_unproven_queries(tt, monkeypatch):
     assert torch.allclose(top_s, ref_s, atol=1e-6)
 
 
-def test_scan_tensor_core_full_shard_properties(tt):
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_scan_tensor_core_full_shard_properties(tt, monkeypatch, pair):
     """1 M x 384 shard, 512 queries: planted neighbours are found, results are reproducible, and sharding the
-    corpus over 4 'GPUs' + merge gives the identical list."""
+    corpus over 4 'GPUs' + merge gives the identical list (both scan kernels)."""
+    monkeypatch.setenv("TT_SCAN_PAIR", pair)
     gen = torch.Generator(device=DEV).manual_seed(5)
     N, Q, P, k = 1_000_000, 512, 384, 10
     De = torch.randn(N, P, generator=gen, device=DEV)

@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(1024) compact_flags_kernel(const int* __restri
   if (threadIdx.x == 0) *qcount = s_base;
 }
 
-int scan_pair_enabled();
+int scan_pair_enabled(int Q, long long N);
 int scan_stagger();
 float scan_eps();
 
@@ -540,7 +540,7 @@ struct ScanPlan {
 int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
   ScanPlan pl{};
   pl.n_qtiles = (Q + TQ - 1) / TQ;
-  pl.pair = (pl.n_qtiles >= 2 && scan_pair_enabled()) ? 1 : 0;
+  pl.pair = (pl.n_qtiles >= 2 && scan_pair_enabled(Q, N)) ? 1 : 0;
   if (pl.pair) pl.n_qtiles = (pl.n_qtiles + 1) / 2 * 2;
   pl.KB = (P + BK - 1) / BK;
   const long long tiles = (N + TD - 1) / TD;
@@ -584,9 +584,15 @@ int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
   return 0;
 }
 
-int scan_pair_enabled() {
-  const char* e = getenv("TT_SCAN_PAIR");  // tuning hook: 1 selects the cta_group::2 kernel (measured slower so far)
-  return e ? atoi(e) : 0;
+// cta_group::2 scan tiles (256 queries per CTA pair, each document tile loaded once per pair and multicast): measured on
+// B200 with 100k queries — 8.8 M documents 580 vs 634 ms per pass (the scan then sits at the power cap, and the pair
+// moves half the bytes per flop from L2), 4.4 M 301 vs 297 ms, 2.2 M 162 vs 144, 1.1 M 91 vs 74 (the pair halves the
+// number of CTAs, and short shards cannot fill the waves with them).  So: pairs for long shards with many query tiles.
+// TT_SCAN_PAIR=0 / 1 forces either.
+int scan_pair_enabled(int Q, long long N) {
+  const char* e = getenv("TT_SCAN_PAIR");
+  if (e) return atoi(e);
+  return (N >= 6000000 && Q >= 4096) ? 1 : 0;
 }
 
 int scan_stagger() {
