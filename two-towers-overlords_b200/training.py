@@ -213,12 +213,12 @@ class FusedTrainer:
         # TWO step workspaces: the pooled gather of step i+1 (tokens + frozen tables only, never the projection
         # weights) runs beside everything else of step i, so consecutive steps alternate between them
         # How the projection chain is launched (tt_step_args.chain).  Default: the persistent chain kernel — everything
-        # after the pooled gather in ONE launch (129 us alone at configs[1] against 157 us for one kernel per
+        # after the pooled gather in ONE launch (123 us alone at configs[1] against 157 us for one kernel per
         # contraction).  It wants every SM, so nothing runs beside it: on one GPU a step is gather -> chain in one stream
-        # (2 launches, the second a programmatic dependent of the first; 0.2466 ms), under data parallelism the NEXT
+        # (2 launches, the second a programmatic dependent of the first; 0.239 ms), under data parallelism the NEXT
         # step's gather runs beside the exchange kernel, which mostly waits (N = 2: 0.272 ms).  The per-kernel chain
         # (TT_CHAIN=0) lets the look-ahead gather's CTAs slip between its small kernels instead; since the chain kernel
-        # lost its transposed copies that schedule is the slower one (0.2480 ms; N = 2: 0.275 ms).  A trainable table
+        # lost its transposed copies that schedule is the slower one (0.242-0.248 ms; N = 2: 0.275 ms).  A trainable table
         # has no look-ahead in either mode (the gather reads the table the step updates).
         env_chain = os.environ.get("TT_CHAIN")
         if env_chain is not None:
@@ -329,9 +329,9 @@ class FusedTrainer:
                               self.exchange_ctas)
 
     def _pipelined(self, slot: int, next_slot: Optional[int], parity: int):
-        """{rest of step `slot` -> Adam / fused exchange}  ||  {pooled gather of `next_slot` into the other workspace}.
-        The gather is bandwidth work on many small CTAs, the rest is a chain of latency-bound tensor-core kernels:
-        side by side the gather disappears behind the chain (bench: 287 -> 182 us per step on one B200)."""
+        """One training step on the current stream, in the schedule __init__ chose: whole step (gather -> persistent
+        chain kernel), per-kernel chain beside the look-ahead gather of `next_slot`, or — data parallel — persistent
+        chain, then the exchange beside the look-ahead gather."""
         cur = torch.cuda.current_stream()
         fused_opt = self.xchg is None and self.world == 1
         if self._whole_step():
