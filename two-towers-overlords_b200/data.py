@@ -363,6 +363,8 @@ class DeviceTripletFeeder:
         # a trainer that reuses the positives' pooled rows for the in-batch negatives wants their indices in its slot
         neg_bufs = getattr(trainer, "neg_bufs", None)
         neg_ptr = N.ptr(neg_bufs[slot]) if neg_bufs is not None else (N.ptr(self.neg) if want_neg else None)
+        if neg_bufs is not None:
+            trainer._neg_loaded[slot] = True
         step_seed = (self.seed * 0x9E3779B1 + self.epoch * 0x85EBCA77 + step) & 0xFFFFFFFFFFFFFFFF
         N.check(N.load().tt_assemble_triplets(
             ctypes.byref(self.q_desc), ctypes.byref(self.d_desc), N.ptr(self.pair_q), N.ptr(self.pair_d),

@@ -253,6 +253,7 @@ class FusedTrainer:
             if world_size > 1:
                 raise ValueError("in_batch_negatives: the negatives of a data-parallel slice name documents of other ranks")
             self.neg_bufs = [torch.zeros(batch_size, dtype=torch.int32, device=dev) for _ in self.tok_slots]
+            self._neg_loaded = [False] * len(self.tok_slots)  # step() refuses a slot whose indices were never given
             for so in self.step_objs:
                 for slot, buf in enumerate(self.neg_bufs):
                     so.set_neg_index(slot, buf)
@@ -319,6 +320,7 @@ class FusedTrainer:
     def load_neg_index(self, neg_index: torch.Tensor, slot: int = 0):
         """Indices of the in-batch negatives of the batch in `slot` (int [B]; host or device), async on the current stream."""
         self.neg_bufs[slot].copy_(neg_index.to(torch.int32), non_blocking=True)
+        self._neg_loaded[slot] = True
 
     def _fwd_bwd(self, slot: int = 0, phases: int = 0, parity: int = 0, optimise: bool = False):
         self.step_objs[parity].run(slot, phases, optimise=optimise)
@@ -453,6 +455,9 @@ class FusedTrainer:
         its pooled gather then runs beside this step and the following step(next_slot, ...) skips it."""
         if not self._warm:
             self._warm_up()
+        if self.neg_bufs is not None and not self._neg_loaded[slot]:
+            raise RuntimeError(f"FusedTrainer(in_batch_negatives=True): no negative indices were loaded for slot {slot} "
+                               "(load_neg_index / DeviceTripletFeeder.assemble)")
         if self.train_table:
             next_slot = None  # a trainable table changes between steps: its gather cannot run ahead of the update
         lib = ops.N.load()
