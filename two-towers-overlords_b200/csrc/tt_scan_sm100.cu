@@ -368,54 +368,85 @@ __global__ void __launch_bounds__(kRefineThreads)
   __syncthreads();
   if (tid == 0) s_bmax = fmaxf(fmaxf(red_v[0], red_v[1]), fmaxf(red_v[2], red_v[3]));
   __syncthreads();
-  // a. k-th best approximate score: k rounds of "best element after the previous one" in (value desc, slot asc) order
-  for (int r = 0; r < k; ++r) {
-    const float lv = s_last_v;
-    const int lc = s_last_c;
-    float bv = -INFINITY;
-    int bc = -1;
-    for (int c = tid; c < C; c += kRefineThreads) {
-      const float v = approx[c];
-      if (v == -INFINITY) continue;
-      const bool after = v < lv || (v == lv && c > lc);
-      if (after && (bc < 0 || v > bv)) {  // slots ascend within a thread, so the first maximum wins ties
-        bv = v;
-        bc = c;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int c2 = __shfl_xor_sync(0xffffffffu, bc, o);
-      if (c2 >= 0 && (bc < 0 || v2 > bv || (v2 == bv && c2 < bc))) {
-        bv = v2;
-        bc = c2;
-      }
-    }
-    if (lane == 0) {
-      red_v[warp] = bv;
-      red_c[warp] = bc;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      float v = red_v[0];
-      int c = red_c[0];
-      for (int w = 1; w < 4; ++w)
-        if (red_c[w] >= 0 && (c < 0 || red_v[w] > v || (red_v[w] == v && red_c[w] < c))) {
-          v = red_v[w];
-          c = red_c[w];
+  // a. k-th best approximate score.  Every warp first lists the k best of its own slots by itself — k rounds of "best
+  //    element after the previous one" in (value desc, slot asc) order, shuffles only, no block barrier — then warp 0
+  //    takes the k-th best of the 4k listed entries (the k best overall are among them).
+  {
+    float* wl_v = sel_s;  // [4][k] (the selection buffers are not in use yet; k <= 16 by the caller's contract)
+    int* wl_c = sel_c;
+    float lv = INFINITY;
+    int lc = -1;
+    for (int r = 0; r < k; ++r) {
+      float bv = -INFINITY;
+      int bc = -1;
+      for (int c = tid; c < C; c += kRefineThreads) {
+        const float v = approx[c];
+        if (v == -INFINITY) continue;
+        const bool after = v < lv || (v == lv && c > lc);
+        if (after && (bc < 0 || v > bv)) {  // slots ascend within a thread, so the first maximum wins ties
+          bv = v;
+          bc = c;
         }
-      if (c >= 0) {
-        s_last_v = v;
-        s_last_c = c;
-        s_found = r + 1;
-      } else {
-        s_last_v = -INFINITY;
-        s_last_c = C;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int c2 = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (c2 >= 0 && (bc < 0 || v2 > bv || (v2 == bv && c2 < bc))) {
+          bv = v2;
+          bc = c2;
+        }
+      }
+      if (lane == 0) {
+        wl_v[warp * k + r] = bv;
+        wl_c[warp * k + r] = bc;
+      }
+      if (bc >= 0) {
+        lv = bv;
+        lc = bc;
+      } else {  // this warp's slots are exhausted: its remaining entries stay empty
+        lv = -INFINITY;
+        lc = C;
       }
     }
     __syncthreads();
-    if (s_found <= r) break;  // fewer than k candidates exist
+    if (warp == 0) {
+      const int n = 4 * k;  // <= 64: two entries per lane
+      float mv = INFINITY;
+      int mc = -1, found = 0;
+      for (int r = 0; r < k; ++r) {
+        float bv = -INFINITY;
+        int bc = -1;
+        for (int i = lane; i < n; i += 32) {
+          const float v = wl_v[i];
+          const int c = wl_c[i];
+          if (c < 0) continue;
+          const bool after = v < mv || (v == mv && c > mc);
+          if (after && (bc < 0 || v > bv || (v == bv && c < bc))) {
+            bv = v;
+            bc = c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int c2 = __shfl_xor_sync(0xffffffffu, bc, o);
+          if (c2 >= 0 && (bc < 0 || v2 > bv || (v2 == bv && c2 < bc))) {
+            bv = v2;
+            bc = c2;
+          }
+        }
+        if (bc < 0) break;  // fewer than k candidates exist
+        mv = bv;
+        mc = bc;
+        ++found;
+      }
+      if (lane == 0) {
+        s_last_v = mv;
+        s_found = found;
+      }
+    }
+    __syncthreads();
   }
   // b. candidates that can still reach the top k
   const float t = (s_found == k) ? s_last_v - 2.f * eps : -INFINITY;
@@ -435,19 +466,39 @@ __global__ void __launch_bounds__(kRefineThreads)
     const float* qr = Qn + (size_t)q * P;
 #pragma unroll
     for (int i = 0; i < 16; ++i) qv[i] = (lane + 32 * i < P) ? qr[lane + 32 * i] : 0.f;
-    for (int i = warp; i < ns; i += kRefineThreads / 32) {
-      const int c = sel_c[i];
-      const int s = c / KC, j = c - s * KC;
-      const int id = cand_i[((size_t)s * Q + q) * KC + j];
-      const float* dr = Dn + (size_t)id * P;
-      float dot = 0.f;
+    // two candidates per trip: their document rows (random 4 P-byte reads from HBM) are requested together
+    constexpr int kW = kRefineThreads / 32;
+    for (int i = warp; i < ns; i += 2 * kW) {
+      const int i2 = i + kW;
+      const bool two = i2 < ns;
+      const int c0 = sel_c[i], c1 = sel_c[two ? i2 : i];
+      const int s0 = c0 / KC, s1 = c1 / KC;
+      const int id0 = cand_i[((size_t)s0 * Q + q) * KC + (c0 - s0 * KC)];
+      const int id1 = cand_i[((size_t)s1 * Q + q) * KC + (c1 - s1 * KC)];
+      const float* d0 = Dn + (size_t)id0 * P;
+      const float* d1 = Dn + (size_t)id1 * P;
+      float x0[16], x1[16];
 #pragma unroll
-      for (int ii = 0; ii < 16; ++ii)
-        if (lane + 32 * ii < P) dot = fmaf(qv[ii], __ldg(dr + lane + 32 * ii), dot);
-      dot = warp_sum(dot);
+      for (int ii = 0; ii < 16; ++ii) {
+        const bool in = lane + 32 * ii < P;
+        x0[ii] = in ? __ldg(d0 + lane + 32 * ii) : 0.f;
+        x1[ii] = in ? __ldg(d1 + lane + 32 * ii) : 0.f;
+      }
+      float dot0 = 0.f, dot1 = 0.f;
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) {  // same order of the products as one row at a time: same bits
+        dot0 = fmaf(qv[ii], x0[ii], dot0);
+        dot1 = fmaf(qv[ii], x1[ii], dot1);
+      }
+      dot0 = warp_sum(dot0);
+      dot1 = warp_sum(dot1);
       if (lane == 0) {
-        sel_s[i] = dot;
-        sel_id[i] = id;
+        sel_s[i] = dot0;
+        sel_id[i] = id0;
+        if (two) {
+          sel_s[i2] = dot1;
+          sel_id[i2] = id1;
+        }
       }
     }
   }
