@@ -349,10 +349,23 @@ __global__ void __launch_bounds__(kRefineThreads)
   __shared__ int s_last_c, s_found;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = blockIdx.x, C = S * KC;
-  for (int c = tid; c < C; c += kRefineThreads) {
-    const int s = c / KC, j = c - s * KC;
-    const size_t idx = ((size_t)s * Q + q) * KC + j;
-    approx[c] = cand_i[idx] >= 0 ? cand_s[idx] : -INFINITY;
+  for (int c0 = tid; c0 < C; c0 += 4 * kRefineThreads) {  // four slots per trip: eight independent loads in flight
+    int ci[4];
+    float cs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * kRefineThreads;
+      const int cc = c < C ? c : tid;  // (a slot of this thread that exists: keeps the loads unconditional)
+      const int s = cc / KC, j = cc - s * KC;
+      const size_t idx = ((size_t)s * Q + q) * KC + j;
+      ci[u] = __ldg(cand_i + idx);
+      cs[u] = __ldg(cand_s + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * kRefineThreads;
+      if (c < C) approx[c] = ci[u] >= 0 ? cs[u] : -INFINITY;
+    }
   }
   float bm = -INFINITY;
   for (int s = tid; s < S; s += kRefineThreads) bm = fmaxf(bm, bound[(size_t)s * Q + q]);
