@@ -47,8 +47,22 @@ struct alignas(64) ScanParams {
   long long N, docs_per_split;
   float* cand_s;   // [S, Q, KC] approximate scores (diagnostic / tie information)
   int* cand_i;     // [S, Q, KC] local document index, -1 = empty
-  float* bound;    // [S, Q] KC-th best approximate score of the split, -inf if fewer than KC documents
+  float* bound;    // [S, Q] final append threshold of the split: every document outside its list scored <= this
+  // Shared floor of the append thresholds, one per query (float bits; 0xffffffff = none yet).  A split that has seen k
+  // documents publishes its k-th best approximate score t: at least k documents of the corpus score >= t, so the exact
+  // k-th best is >= t - eps and a document whose approximate score is below t - 3 eps can be neither in the result nor
+  // needed for the completeness proof (refine_kernel checks max bound + eps < exact k-th best; here bound + eps <=
+  // t - 2 eps).  Every split raises its own threshold to the floor, so short splits stop appending as soon as ANY
+  // split has found good documents (without it a split of a few thousand documents never settles).
+  unsigned* gthr;  // [Q]
+  int k;
+  float eps;
 };
+
+__device__ __forceinline__ void atomic_max_float(unsigned* addr, float v) {  // works from the 0xffffffff start value
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(addr, __float_as_uint(v));
+}
 
 // PAIR = true: two CTAs (a cluster of 2 along the query tiles) drive one cta_group::2 MMA of 256 queries x 128 documents:
 // each CTA holds its own 128 queries in TMEM and streams only 64 of the 128 documents of a tile, so the L2 and
@@ -236,17 +250,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_candidates_kernel(const 
       }
       if (cnt >= KC) {
         cnt = KC;
-        thr = ls[(KC - 1) * TQ];
+        thr = fmaxf(thr, ls[(KC - 1) * TQ]);
       }
+      if (q_ok && cnt >= p.k) atomic_max_float(p.gthr + q0 + t_row, ls[(p.k - 1) * TQ]);  // (the list is sorted now)
     };
+    const float floor_margin = 3.f * p.eps;
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
+      // the shared floor is looked at after tiles 1, 2, 4, 8 and then every 16th (it moves fast only at the start); the
+      // load is issued before the wait for the accumulator so that its latency is not on the tile's path
+      const bool floor_due = q_ok && (((t & (t - 1)) == 0 && t < 16) || (t & 15) == 0);
+      float floor_g = 0.f;
+      if (floor_due) floor_g = __uint_as_float(*reinterpret_cast<volatile const unsigned*>(p.gthr + q0 + t_row));
       mbar_wait(&tmem_full[buf], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       int tt_ = t + stagger;
       if (tt_ >= n_tiles) tt_ -= n_tiles;
       const int d0 = tt_ * TD;  // local to the split
       const int nd = (int)min((long long)TD, d_end - d_beg - d0);
+      if (floor_due) thr = fmaxf(thr, floor_g - floor_margin);  // (a NaN start value leaves thr alone)
       // 4 chunks of 32 scores, double-buffered in registers: the TMEM load of chunk c+1 flies while chunk c is scanned
       const uint32_t t_addr = tmem_base + (uint32_t)(buf * TD) + ((uint32_t)(qd * 32) << 16);
       uint32_t ra[32], rb[32];
@@ -675,6 +697,7 @@ struct ScanWs {
   int* cand_i;
   float* bound;
   int *flag, *qlist, *qcount;
+  unsigned* gthr;
   void* listed;
 };
 
@@ -688,6 +711,7 @@ size_t carve_scan(char* base, const ScanPlan& pl, int Q, int k, ScanWs* out) {
   w.flag = ws_take<int>(p, Q);
   w.qlist = ws_take<int>(p, Q);
   w.qcount = ws_take<int>(p, 64);
+  w.gthr = ws_take<unsigned>(p, Q);
   w.listed = ws_take<char>(p, scan_listed_ws_bytes(pl.cap, k));
   if (out) *out = w;
   return (size_t)(p - base) + 256;
@@ -728,6 +752,8 @@ int scan_topk_sm100(const float* Qn, const float* Dn, const void* Qb, const void
   sp.Q = Q; sp.P = P; sp.KB = pl.KB; sp.KC = pl.KC; sp.stages = pl.stages;
   sp.N = N; sp.docs_per_split = pl.docs_per_split;
   sp.cand_s = w.cand_s; sp.cand_i = w.cand_i; sp.bound = w.bound;
+  sp.gthr = w.gthr; sp.k = k; sp.eps = scan_eps();
+  TT_CUDA(cudaMemsetAsync(w.gthr, 0xff, (size_t)Q * sizeof(unsigned), st));
   if (pl.pair) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pl.n_qtiles, pl.S);
