@@ -671,14 +671,14 @@ int make_plan(int Q, long long N, int P, int k, ScanPlan* out) {
 }
 
 // cta_group::2 scan tiles (256 queries per CTA pair, each document tile loaded once per pair and multicast): measured on
-// B200 with 100k queries — 8.8 M documents 580 vs 634 ms per pass (the scan then sits at the power cap, and the pair
-// moves half the bytes per flop from L2), 4.4 M 301 vs 297 ms, 2.2 M 162 vs 144, 1.1 M 91 vs 74 (the pair halves the
-// number of CTAs, and short shards cannot fill the waves with them).  So: pairs for long shards with many query tiles.
-// TT_SCAN_PAIR=0 / 1 forces either.
+// B200 with 100k queries (ms per pass, pair vs one CTA) — 8.8 M documents 577 vs 634 (the scan sits at the power cap, and
+// the pair moves half the bytes per flop from L2: 52 GB instead of 1.3 TB of DRAM traffic), 4.4 M 292 vs 321-345,
+// 2.2 M 153 vs 153, 1.1 M 79 vs 68 (the pair halves the number of CTAs, and short shards cannot fill the waves with
+// them).  So: pairs for shards of 3 M documents and more with many query tiles.  TT_SCAN_PAIR=0 / 1 forces either.
 int scan_pair_enabled(int Q, long long N) {
   const char* e = getenv("TT_SCAN_PAIR");
   if (e) return atoi(e);
-  return (N >= 6000000 && Q >= 4096) ? 1 : 0;
+  return (N >= 3000000 && Q >= 4096) ? 1 : 0;
 }
 
 int scan_stagger() {
