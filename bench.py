@@ -1026,8 +1026,8 @@ def run_scan(dev, world, rank, n_docs, n_queries, P, passes, precision="bf16"):
                                if (n_local == 8_800_000 and P == 384) else None,
                                "note": "one 128-query tile against the whole bf16 shard (N_local*P*2 algorithmic "
                                        "bytes); timed over the WHOLE search call (normalise + scan kernel + refine/"
-                                       "re-score + flag compaction, 6 launches), the scan kernel alone is 1.07 ms "
-                                       "under ncu (profiles/r01_ncu_summary.json); passes/s = the reference's "
+                                       "re-score + flag compaction; one CUDA-graph replay), the scan kernel alone is 1.01 ms "
+                                       "under ncu and reads the shard exactly once (profiles/r02_ncu_summary.json); passes/s = the reference's "
                                        "per-query eval regime"},
     }
 
