@@ -272,13 +272,18 @@ __global__ void __launch_bounds__(kPoolThreads) pool_fwd_kernel(const PoolParams
   }
 }
 
-int pool_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TT_POOL_VARIANT");  // tuning hook: 0 = register-pipelined x4, 1 = x4 (default: 54 regs, 36 warps/SM), 2 = x8, 3 = pipelined x2
-    v = e ? atoi(e) : 1;
+// Rows in flight per warp.  TT_POOL_VARIANT (tuning hook): 0 = register-pipelined x4, 1 = x4 (36 warps per SM),
+// 2 = x8, 3 = pipelined x2.  Default: x8 for fp32 tables when the gather has the SMs to itself (whole-step calls:
+// 100.5 vs 103 us per launch, 0.2373 vs 0.2407 ms per configs[1] step), x4 when it shares them with other kernels
+// (more, lighter warps interleave better) and for bf16 tables.
+int pool_variant(bool share_sm, bool fp32_table) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("TT_POOL_VARIANT");
+    env = e ? atoi(e) : -1;
   }
-  return v;
+  if (env >= 0) return env;
+  return (!share_sm && fp32_table) ? 2 : 1;
 }
 
 // Unused dynamic shared memory that caps how many gather CTAs an SM holds.  When the gather of step i+1 runs beside the
@@ -301,7 +306,7 @@ template <typename TE, int NV>
 int launch_pool(const PoolParams& p, int total, cudaStream_t st) {
   constexpr int UNROLL = sizeof(TE) == 4 ? 4 : 8;
   const size_t pad = pool_pad_smem(p.share_sm != 0);
-  switch (pool_variant()) {
+  switch (pool_variant(p.share_sm != 0, sizeof(TE) == 4)) {
     case 1: pool_fwd_kernel<TE, NV, UNROLL, false><<<total, kPoolThreads, pad, st>>>(p); break;
     case 2: pool_fwd_kernel<TE, NV, UNROLL * 2, false><<<total, kPoolThreads, pad, st>>>(p); break;
     case 3: pool_fwd_kernel<TE, NV, UNROLL / 2, true><<<total, kPoolThreads, pad, st>>>(p); break;
